@@ -1,0 +1,174 @@
+/*
+ * shg.h -- C ABI of libshg.so: the B200 (sm_100a) kernels behind the
+ * Solex_ser_recon frame-stack reconstruction path.
+ *
+ * The reference (thelondonsmiths/Solex_ser_recon_EN) is pure Python and has no
+ * FFI of its own: the drop-in boundary is its Python callables.
+ * The Python modules in solex_ser_recon_en_b200/ keep those names and
+ * signatures and bind the entry points below with ctypes.
+ * Each entry point cites the reference code whose work it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    available from shg_last_error() (thread-local);
+ *  - pointers named d_* are DEVICE pointers, h_* are HOST pointers; sizes are
+ *    in elements unless the name says bytes;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *    kernels are asynchronous on it, nothing here synchronises unless stated;
+ *  - a raw frame is H rows x W columns exactly as stored in the SER/AVI file;
+ *    "rotated" (W > H) means the reference image is np.rot90(raw):
+ *    img[i][j] = raw[j][W-1-i], ih = W slit positions, iw = H dispersion pixels
+ *    (reference video_reader.py:84-91,117-120);
+ *  - "disk" images are produced FRAME-MAJOR: disk[s][k][i] (shift, frame, slit
+ *    position), i.e. the transpose of the reference's (ih, N) arrays, so that
+ *    every kernel reads and writes contiguous runs; shg_transpose_u16 gives the
+ *    reference layout where it is handed back to Python.
+ */
+#ifndef SHG_H
+#define SHG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHG_VERSION 1
+
+/* ---- status / device ---------------------------------------------------- */
+const char* shg_last_error(void);
+int shg_version(void);
+/* out[0]=sm count, out[1]=cc major, out[2]=cc minor, out[3]=total HBM bytes,
+ * out[4]=L2 bytes, out[5]=max opt-in shared memory per block */
+int shg_device_info(int device, int64_t* out6);
+
+/* ---- a3: mean / max frame (reference solex_util.py:174-188) ------------- */
+/* Add frames [0,n_frames) of d_frames (contiguous, frame_px pixels each,
+ * bytes_per_px 1 or 2, raw file units) into d_sum[frame_px] (uint64) and
+ * d_max[frame_px] (uint32).  Integer atomics: the result does not depend on
+ * launch geometry; partial results of frame ranges / ranks add exactly. */
+int shg_accumulate(const void* d_frames, int bytes_per_px, int64_t n_frames, int64_t frame_px,
+                   uint64_t* d_sum, uint32_t* d_max, void* stream);
+
+/* mean = floor(scale*sum / n_total), max = scale*max (scale = 256 for 8-bit
+ * input: reference video_reader.py:121-122), written in IMAGE orientation
+ * (ih x iw, rotated when W > H) as uint16. */
+int shg_finalize_mean_max(const uint64_t* d_sum, const uint32_t* d_max, int64_t n_total,
+                          int W, int H, int eight_bit,
+                          uint16_t* d_mean_img, uint16_t* d_max_img, void* stream);
+
+/* ---- a4/a5: line detection (reference solex_util.py:165-172,223-231,242) */
+/* cv2.blur(img, (kw, kh)) on uint16 as OpenCV 4.13 computes it: exact box sum,
+ * BORDER_REFLECT_101, anchor k/2, rint(float32(S)*float32(1/(kw*kh))) for
+ * columns < cols - cols%8 and rint(S*(1.0/(kw*kh))) in double for the rest.
+ * d_tmp: scratch of rows*cols uint32. */
+int shg_box_blur_u16(const uint16_t* d_img, int rows, int cols, int kw, int kh,
+                     uint16_t* d_out, uint32_t* d_tmp, void* stream);
+/* per-row integer sums (for np.mean(blur, axis=1)) */
+int shg_row_sums_u16(const uint16_t* d_img, int rows, int cols, uint64_t* d_out, void* stream);
+/* per-row FIRST argmin over columns [c0, c1) -> absolute column index */
+int shg_row_argmin_u16(const uint16_t* d_img, int rows, int cols, int c0, int c1,
+                       int32_t* d_out, void* stream);
+
+/* ---- a6: cubic least-squares fit (reference solex_util.py:233-259) ------ */
+/* Masked cubic fit of y[i] against x = x0 + i, i in [0,n): fp64 moment sums
+ * reduced with warp shuffles, 4x4 solve on the device.  d_mask may be NULL.
+ * d_coef[4]: ascending coefficients in raw x (as np.flip(np.polyfit(...))).
+ * Optionally (d_resid != NULL) writes resid[i] = polyval(x0+i) - y_resid[i]. */
+int shg_polyfit3(const int32_t* d_y, const uint8_t* d_mask, int x0, int n,
+                 double* d_coef, const int32_t* d_y_resid, double* d_resid, void* stream);
+/* keep[i] = |resid[i] / std(resid)| < nsigma   (np.std, ddof 0) */
+int shg_sigma_mask(const double* d_resid, int n, double nsigma, uint8_t* d_keep, void* stream);
+/* good[i] = |resid[i] - centre| < tol */
+int shg_window_mask(const double* d_resid, int n, double centre, double tol, uint8_t* d_good, void* stream);
+/* fit table rows [floor(c), c-floor(c), y, c], c = polyval(y), y in [0,ih) */
+int shg_fit_table(const double* d_coef, int ih, double* d_fit /* ih x 4 */, void* stream);
+
+/* ---- a7: per-frame reconstruction (reference solex_util.py:93-144) ------ */
+/* For every frame k, shift s, slit position i:
+ *   il = clamp((int)fit[i][0] + shift[s], 0, iw-2)
+ *   disk[s][k][i] = trunc(L*lw + R*rw), L/R = img_k[i][il], img_k[i][il+1]
+ *   lw = 1 - fit[i][1], rw = 1 - lw   (fp64, separate mul/mul/add)
+ * 8-bit input is scaled by 256.  h_fit is the HOST (ih x 4) fit table exactly
+ * as read_video_improved receives it.  d_disk is frame-major; element (s,k,i)
+ * lives at d_disk[s*shift_stride + (k0_out+k)*ih + i].  d_work: device scratch
+ * of at least shg_recon_workspace_bytes(ih, n_shifts) bytes.
+ * impl: 0 = auto, 1 = generic direct-load kernel, 2 = TMA band kernel. */
+int64_t shg_recon_workspace_bytes(int ih, int n_shifts);
+int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
+              const double* h_fit, const int32_t* h_shifts, int n_shifts,
+              uint16_t* d_disk, int64_t shift_stride, int64_t k0_out, int impl,
+              void* d_work, int64_t work_bytes, void* stream);
+
+/* ---- layout helpers ------------------------------------------------------ */
+/* out[c][r'] = in[r][c] for in of shape (rows, cols); flip != 0 reverses the
+ * output's fastest axis (r' = rows-1-r): frame-major disk -> reference (ih, N)
+ * layout, with the reference's flip_x (Solex_recon.py:75-76) fused. */
+int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t cols, uint16_t* d_out, int flip, void* stream);
+/* d_out[0]=min, d_out[1]=max of n uint16 values (d_out must be preset to {65535,0}) */
+int shg_minmax_u16(const uint16_t* d_in, int64_t n, uint32_t* d_out2, void* stream);
+
+/* ---- a10: circularisation warp (reference ellipse_to_circle.py:94-118) -- */
+/* Per-row 1-D linear resample of a frame-major disk (n_frames x ih):
+ *   x = (m00*c + m01*r) + m02; out[r][c] = trunc(clip((1-d)*in[floor x][r] + d*in[ceil x][r]))
+ * taps outside [0,n_frames) (or rows >= ih) read cval; clip to [lo,hi] as
+ * skimage.transform.warp does; output row-major (out_rows x out_cols).
+ * flip != 0 reads the disk with its frame axis reversed (flip_x). */
+int shg_warp_rows(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
+                  double m00, double m01, double m02, double cval, double lo, double hi,
+                  uint16_t* d_out, int out_rows, int out_cols, void* stream);
+
+/* ---- a11 helper: 4x4 block sums (reference ellipse_to_circle.py:301) ---- */
+/* downscale_local_mean numerator: out[ri][ci] = sum of the 4x4 block of the
+ * (ih, n_frames) image (zero padded), from a frame-major disk. */
+int shg_downscale4_sum(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
+                       uint32_t* d_out, int out_rows, int out_cols, void* stream);
+
+/* ---- a12: transversalium (reference solex_util.py:76-86,383-395,489-516) */
+/* tab[v] = log(v) for v in [0, 65536) (tab[0] = -inf): pixels are uint16, so
+ * the reference's log(img[y]/img[y-1]) is tab[a] - tab[b] to ~2e-15 absolute. */
+int shg_log_table(double* d_tab65536, void* stream);
+/* For each listed row y (rows[j]), over columns [xa[j], xb[j]):
+ *   rat = log(img[y][x] / img[y-1][x]);  out[j] = mean(rat[|rat-med|/MAD < 2])
+ * (median / MAD as np.median; MAD == 0 keeps all; an empty chord or a nan
+ * gives nan as in the reference).  One CTA per row, exact order statistics by
+ * radix select in shared memory.  max_len = max(xb-xa).  Chords longer than
+ * shared memory holds use d_work (shg_transv_workspace_bytes; 0 = not needed). */
+int64_t shg_transv_workspace_bytes(int n_list, int max_len);
+int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols,
+                         const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,
+                         int max_len, const double* d_logtab, double* d_out,
+                         void* d_work, int64_t work_bytes, void* stream);
+/* out[r][c] = trunc(min(img[r][c] * gain[r], 65535)) */
+int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, const double* d_gain,
+                      uint16_t* d_out, void* stream);
+
+/* ---- a1/a2: ingest (reference video_reader.py:94-123) ------------------- */
+/* Streams frames of a file into a device-resident stack through a ring of
+ * pinned host buffers filled by reader threads (pread), with the H2D copies on
+ * a private copy stream and, when d_sum/d_max are given, the mean/max
+ * accumulation of each chunk overlapped on a private compute stream.
+ * frame_stride_bytes > frame_bytes skips per-frame container headers (AVI). */
+typedef struct shg_ingest shg_ingest;
+int shg_ingest_create(int device, int64_t slot_bytes, int n_slots, int n_threads, shg_ingest** out);
+int shg_ingest_destroy(shg_ingest* ing);
+/* Blocking.  Reads frames [frame0, frame0+n_frames) of `path`.  h_stats[0..3]:
+ * seconds total, seconds waiting on the file, bytes copied, chunks. */
+int shg_ingest_file(shg_ingest* ing, const char* path, int64_t payload_offset,
+                    int64_t frame_bytes, int64_t frame_stride_bytes, int64_t frame0, int64_t n_frames,
+                    void* d_stack, int bytes_per_px, uint64_t* d_sum, uint32_t* d_max, double* h_stats4);
+/* Same pipeline from a host memory image of the payload (e.g. an mmap). */
+int shg_ingest_memory(shg_ingest* ing, const void* h_payload, int64_t frame_bytes,
+                      int64_t frame_stride_bytes, int64_t n_frames, void* d_stack, int bytes_per_px,
+                      uint64_t* d_sum, uint32_t* d_max, double* h_stats4);
+
+/* ---- synthetic scans on the device (bench / full-size property tests) --- */
+/* Fills frames [k0, k0+n) of a synthetic scan of n_total frames (same recipe
+ * family as solex_ser_recon_en_b200/synth.py, hash noise). */
+int shg_synth_fill(void* d_frames, int bytes_per_px, int64_t k0, int64_t n, int64_t n_total,
+                   int W, int H, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHG_H */

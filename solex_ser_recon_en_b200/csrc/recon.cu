@@ -1,0 +1,408 @@
+// Pass 2: per-frame reconstruction along the fitted line at every shift.
+// Replaces the reference's frame x shift loop (solex_util.py:111-134):
+//   ind_l = clip(int(fit[:,0] + shift), 0, iw-2); ind_r = ind_l + 1
+//   disk[s][:, k] = img[arange(ih), ind_l]*lw + img[arange(ih), ind_r]*rw   (float64, truncated)
+//
+// Two kernels:
+//  * recon_generic_kernel -- direct global loads, any geometry (also the
+//    non-rotated H >= W case); the first-correct path and the fallback for
+//    shapes TMA cannot describe (row pitch not a multiple of 16 bytes).
+//  * recon_tma_kernel     -- rotated scans.  In raw coordinates the taps of all
+//    shifts for slit column x live in a short run of raw rows around the line,
+//    so a CTA stages [rows of the band] x [TX columns] of one frame into shared
+//    memory with one TMA box per run of shifts (cp.async.bulk.tensor, mbarrier
+//    completion, multi-stage ring), and every thread walks its column through
+//    all shifts.  HBM traffic = band rows once + outputs once.
+// Bound: HBM.  Algorithmic bytes / frame = ih*nb*bytes_per_px + n_shifts*ih*2.
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxShifts = 512;
+constexpr int kMaxRuns = 8;
+constexpr int kMaxBoxRows = 256;
+
+struct ShiftTable {
+    int n_shifts;
+    int n_runs;
+    int run_first[kMaxRuns + 1];   // [run] -> first index into sh/slot (sorted by shift)
+    int run_rows[kMaxRuns];        // TMA box height of the run
+    int run_off[kMaxRuns];         // element offset of the run inside one stage
+    short sh[kMaxShifts];
+    short slot[kMaxShifts];        // output image index of sh[j]
+};
+
+struct TmaMaps {
+    CUtensorMap m[kMaxRuns];
+};
+
+template <typename T>
+__device__ __forceinline__ double px_to_double(T v);
+template <>
+__device__ __forceinline__ double px_to_double<uint16_t>(uint16_t v) { return u32_to_double(v); }
+template <>
+__device__ __forceinline__ double px_to_double<uint8_t>(uint8_t v) { return u32_to_double((uint32_t)v << 8); }
+
+__device__ __forceinline__ uint16_t lerp_trunc(double L, double R, double lw, double rw) {
+    // (L*lw) + (R*rw), each rounded to nearest: no fma contraction
+    return (uint16_t)double_floor_to_u32(__dadd_rn(__dmul_rn(L, lw), __dmul_rn(R, rw)));
+}
+
+// ---------------------------------------------------------------------------
+template <typename T, bool ROT>
+__global__ void __launch_bounds__(256)
+recon_generic_kernel(const T* __restrict__ frames, int64_t n_frames, int W, int H,
+                     const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
+                     const __grid_constant__ ShiftTable tab, uint16_t* __restrict__ disk, int64_t shift_stride,
+                     int64_t k0_out) {
+    const int ih = ROT ? W : H, iw = ROT ? H : W;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ih) return;
+    const int i = ROT ? (W - 1 - t) : t;          // ROT: thread t is raw column x = t
+    const int f = fl[i];
+    const double wl = lw[i], wr = rw[i];
+    for (int64_t k = blockIdx.y; k < n_frames; k += gridDim.y) {
+        const T* fr = frames + k * (int64_t)H * W;
+        uint16_t* out = disk + (k0_out + k) * ih + i;
+        for (int j = 0; j < tab.n_shifts; ++j) {
+            const int il = min(max(f + tab.sh[j], 0), iw - 2);
+            T a, b;
+            if (ROT) {
+                a = fr[(int64_t)il * W + t];
+                b = fr[(int64_t)(il + 1) * W + t];
+            } else {
+                a = fr[(int64_t)t * W + il];
+                b = fr[(int64_t)t * W + il + 1];
+            }
+            out[tab.slot[j] * shift_stride] = lerp_trunc(px_to_double<T>(a), px_to_double<T>(b), wl, wr);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA / mbarrier plumbing (inline PTX; see the Blackwell guide, TMA + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+        "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <typename T, int TX, int STAGES>
+__global__ void __launch_bounds__(TX)
+recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ShiftTable tab,
+                 int64_t n_frames, int W, int H, int n_tx, int stage_elems,
+                 const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
+                 const int* __restrict__ row0 /* [n_tx][n_runs] */,
+                 uint16_t* __restrict__ disk, int64_t shift_stride, int64_t k0_out) {
+    extern __shared__ unsigned char smem_raw[];
+    // TMA destinations want 128-byte alignment; the launch reserves the slack
+    T* stage_buf = reinterpret_cast<T*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    __shared__ __align__(8) uint64_t full[STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = n_frames * n_tx;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t stage_bytes = (uint32_t)stage_elems * sizeof(T);
+
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int stage) {
+        const int tx = (int)(tile % n_tx);
+        const int k = (int)(tile / n_tx);
+        mbar_expect_tx(&full[stage], stage_bytes);
+        T* dst = stage_buf + (size_t)stage * stage_elems;
+        for (int r = 0; r < tab.n_runs; ++r)
+            tma_load_3d(dst + tab.run_off[r], &maps.m[r], &full[stage], tx * TX, row0[tx * tab.n_runs + r], k, policy);
+    };
+
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s)
+            if (first + s * stride < n_tiles) issue(first + s * stride, s);
+
+    const int iw = H;
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+        const int stage = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        const int tx = (int)(tile % n_tx);
+        const int64_t k = tile / n_tx;
+        const int x = tx * TX + tid;
+        const bool live = x < W;
+        const int i = W - 1 - x;
+        int f = 0;
+        double wl = 0.0, wr = 0.0;
+        if (live) { f = fl[i]; wl = lw[i]; wr = rw[i]; }
+
+        mbar_wait(&full[stage], phase);
+
+        if (live) {
+            const T* buf = stage_buf + (size_t)stage * stage_elems + tid;
+            uint16_t* out = disk + (k0_out + k) * W + i;
+            for (int r = 0; r < tab.n_runs; ++r) {
+                const T* rb = buf + tab.run_off[r];
+                const int base = row0[tx * tab.n_runs + r];
+                const int j1 = tab.run_first[r + 1];
+                for (int j = tab.run_first[r]; j < j1; ++j) {
+                    const int il = min(max(f + tab.sh[j], 0), iw - 2) - base;
+                    const T a = rb[il * TX];
+                    const T b = rb[(il + 1) * TX];
+                    out[tab.slot[j] * shift_stride] = lerp_trunc(px_to_double<T>(a), px_to_double<T>(b), wl, wr);
+                }
+            }
+        }
+        __syncthreads();                                  // everyone is done with this stage
+        if (tid == 0) {
+            const int64_t nxt = tile + (int64_t)STAGES * stride;
+            if (nxt < n_tiles) issue(nxt, stage);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SHG_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        SHG_REQUIRE(p && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+        cached = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *fn = cached;
+    return 0;
+}
+
+struct HostPlan {
+    ShiftTable tab;
+    std::vector<int> fl;
+    std::vector<double> lw, rw;
+    std::vector<int> row0;     // [n_tx][n_runs]
+    int n_tx = 0, tx = 0, stage_elems = 0;
+    bool tma_ok = false;
+};
+
+// Sort shifts, group them into runs of nearby shifts (one TMA box each).
+void build_runs(const int32_t* shifts, int n, int max_rows, ShiftTable& tab, std::vector<std::pair<int, int>>& order) {
+    order.resize(n);
+    for (int j = 0; j < n; ++j) order[j] = {shifts[j], j};
+    std::stable_sort(order.begin(), order.end());
+    tab.n_shifts = n;
+    for (int j = 0; j < n; ++j) { tab.sh[j] = (short)order[j].first; tab.slot[j] = (short)order[j].second; }
+    // greedy: start a new run when the gap to the previous shift is large or the run gets too tall
+    std::vector<int> firsts{0};
+    for (int j = 1; j < n; ++j) {
+        const int gap = order[j].first - order[j - 1].first;
+        const int span = order[j].first - order[firsts.back()].first;
+        if (gap > 6 || span + 2 > max_rows) firsts.push_back(j);
+    }
+    // too many runs: merge the closest neighbours until they fit
+    while ((int)firsts.size() > kMaxRuns) {
+        int best = 1, best_gap = 1 << 30;
+        for (size_t r = 1; r < firsts.size(); ++r) {
+            const int gap = order[firsts[r]].first - order[firsts[r] - 1].first;
+            if (gap < best_gap) { best_gap = gap; best = (int)r; }
+        }
+        firsts.erase(firsts.begin() + best);
+    }
+    tab.n_runs = (int)firsts.size();
+    for (int r = 0; r < tab.n_runs; ++r) tab.run_first[r] = firsts[r];
+    tab.run_first[tab.n_runs] = n;
+}
+
+}  // namespace
+
+extern "C" int64_t shg_recon_workspace_bytes(int ih, int n_shifts) {
+    // fl + lw + rw + row0 (worst case one tile per 64 columns, kMaxRuns runs), 256-byte aligned pieces
+    const int64_t a = ((int64_t)ih * 4 + 255) / 256 * 256;
+    const int64_t b = ((int64_t)ih * 8 + 255) / 256 * 256;
+    const int64_t c = (((int64_t)(ih + 63) / 64) * kMaxRuns * 4 + 255) / 256 * 256;
+    (void)n_shifts;
+    return a + 2 * b + c;
+}
+
+extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
+                         const double* h_fit, const int32_t* h_shifts, int n_shifts,
+                         uint16_t* d_disk, int64_t shift_stride, int64_t k0_out, int impl,
+                         void* d_work, int64_t work_bytes, void* stream) {
+    SHG_REQUIRE(bytes_per_px == 1 || bytes_per_px == 2, "shg_recon: bytes_per_px must be 1 or 2");
+    SHG_REQUIRE(n_shifts >= 1 && n_shifts <= kMaxShifts, "shg_recon: %d shifts (max %d)", n_shifts, kMaxShifts);
+    SHG_REQUIRE(W >= 2 && H >= 2, "shg_recon: bad geometry %dx%d", W, H);
+    if (n_frames <= 0) return 0;
+    const bool rot = W > H;
+    const int ih = rot ? W : H, iw = rot ? H : W;
+    SHG_REQUIRE(work_bytes >= shg_recon_workspace_bytes(ih, n_shifts), "shg_recon: workspace too small");
+    for (int j = 0; j < n_shifts; ++j)
+        SHG_REQUIRE(h_shifts[j] > -30000 && h_shifts[j] < 30000, "shg_recon: shift %d out of range", h_shifts[j]);
+    cudaStream_t st = as_stream(stream);
+
+    // ---- host tables (reference solex_util.py:113-123) ----------------------
+    HostPlan plan;
+    plan.fl.resize(ih); plan.lw.resize(ih); plan.rw.resize(ih);
+    for (int i = 0; i < ih; ++i) {
+        double f0 = h_fit[4 * i + 0];
+        f0 = std::min(std::max(f0, -1.0e9), 1.0e9);
+        plan.fl[i] = (int)f0;                          // .astype(int): truncation (value is integral)
+        plan.lw[i] = 1.0 - h_fit[4 * i + 1];
+        plan.rw[i] = 1.0 - plan.lw[i];
+    }
+    std::vector<std::pair<int, int>> order;
+    build_runs(h_shifts, n_shifts, kMaxBoxRows - 8, plan.tab, order);
+
+    // ---- can TMA describe this stack? ---------------------------------------
+    const int64_t row_bytes = (int64_t)W * bytes_per_px;
+    bool tma = rot && impl != 1 && row_bytes % 16 == 0 && ((int64_t)H * row_bytes) % 16 == 0 &&
+               ((uintptr_t)d_frames % 16 == 0) && n_frames < (1LL << 31);
+    int TX = 0, stages = 0;
+    if (tma) {
+        // tile width: as wide as shared memory allows with >= 3 stages
+        for (int cand : {256, 128, 64}) {
+            if (cand > 64 && cand / 2 >= W) continue;
+            const int n_tx = (W + cand - 1) / cand;
+            plan.row0.assign((size_t)n_tx * plan.tab.n_runs, 0);
+            bool ok = true;
+            int elems = 0;
+            for (int r = 0; r < plan.tab.n_runs && ok; ++r) {
+                int rows_needed = 0;
+                for (int t = 0; t < n_tx; ++t) {
+                    int lo = 1 << 30, hi = -(1 << 30);
+                    for (int x = t * cand; x < std::min(W, (t + 1) * cand); ++x) {
+                        const int f = plan.fl[W - 1 - x];
+                        const int a = std::min(std::max(f + plan.tab.sh[plan.tab.run_first[r]], 0), iw - 2);
+                        const int b = std::min(std::max(f + plan.tab.sh[plan.tab.run_first[r + 1] - 1], 0), iw - 2);
+                        lo = std::min(lo, a);
+                        hi = std::max(hi, b + 1);
+                    }
+                    plan.row0[(size_t)t * plan.tab.n_runs + r] = lo;
+                    rows_needed = std::max(rows_needed, hi - lo + 1);
+                }
+                if (rows_needed > kMaxBoxRows) ok = false;
+                plan.tab.run_rows[r] = rows_needed;
+                plan.tab.run_off[r] = elems;
+                elems += ((rows_needed * cand * bytes_per_px + 127) / 128 * 128) / bytes_per_px;
+            }
+            if (!ok) continue;
+            const int64_t sbytes = (int64_t)elems * bytes_per_px;
+            const int max_stages = (int)(200 * 1024 / sbytes);
+            if (max_stages >= 3) {
+                TX = cand; plan.n_tx = n_tx; plan.stage_elems = elems;
+                stages = std::min(max_stages, 4);
+                break;
+            }
+        }
+        if (TX == 0) tma = false;
+    }
+    SHG_REQUIRE(!(impl == 2 && !tma), "shg_recon: TMA path requested but this geometry cannot use it");
+
+    // ---- upload tables --------------------------------------------------------
+    char* w = static_cast<char*>(d_work);
+    const int64_t a = ((int64_t)ih * 4 + 255) / 256 * 256;
+    const int64_t b = ((int64_t)ih * 8 + 255) / 256 * 256;
+    int* d_fl = reinterpret_cast<int*>(w);
+    double* d_lw = reinterpret_cast<double*>(w + a);
+    double* d_rw = reinterpret_cast<double*>(w + a + b);
+    int* d_row0 = reinterpret_cast<int*>(w + a + 2 * b);
+    SHG_CHECK(cudaMemcpyAsync(d_fl, plan.fl.data(), (size_t)ih * 4, cudaMemcpyHostToDevice, st));
+    SHG_CHECK(cudaMemcpyAsync(d_lw, plan.lw.data(), (size_t)ih * 8, cudaMemcpyHostToDevice, st));
+    SHG_CHECK(cudaMemcpyAsync(d_rw, plan.rw.data(), (size_t)ih * 8, cudaMemcpyHostToDevice, st));
+
+    if (!tma) {
+        dim3 grid((ih + 255) / 256, (unsigned)std::min<int64_t>(n_frames, 65535));
+        if (rot && bytes_per_px == 2)
+            recon_generic_kernel<uint16_t, true><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+        else if (rot)
+            recon_generic_kernel<uint8_t, true><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+        else if (bytes_per_px == 2)
+            recon_generic_kernel<uint16_t, false><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+        else
+            recon_generic_kernel<uint8_t, false><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+        SHG_LAUNCH_CHECK();
+        return 0;
+    }
+
+    SHG_CHECK(cudaMemcpyAsync(d_row0, plan.row0.data(), plan.row0.size() * 4, cudaMemcpyHostToDevice, st));
+
+    EncodeTiledFn encode;
+    if (int rc = get_encode_fn(&encode)) return rc;
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int r = 0; r < plan.tab.n_runs; ++r) {
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_frames};
+        cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)H * row_bytes};
+        cuuint32_t box[3] = {(cuuint32_t)TX, (cuuint32_t)plan.tab.run_rows[r], 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult cr = encode(&maps.m[r], bytes_per_px == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                             3, const_cast<void*>(d_frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SHG_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)cr, TX, plan.tab.run_rows[r]);
+    }
+
+    int dev = 0, sms = SHG_SM_COUNT_B200;
+    SHG_CHECK(cudaGetDevice(&dev));
+    SHG_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = (size_t)plan.stage_elems * bytes_per_px * stages + 128;
+    const int64_t n_tiles = n_frames * plan.n_tx;
+    const int ctas_per_sm = std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * ctas_per_sm);
+
+#define SHG_LAUNCH_TMA(T, TXV, ST)                                                                         \
+    do {                                                                                                   \
+        auto kern = recon_tma_kernel<T, TXV, ST>;                                                          \
+        SHG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<grid, TXV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, d_fl,    \
+                                      d_lw, d_rw, d_row0, d_disk, shift_stride, k0_out);                   \
+    } while (0)
+#define SHG_DISPATCH_ST(T, TXV)                                  \
+    do {                                                         \
+        if (stages >= 4) SHG_LAUNCH_TMA(T, TXV, 4);              \
+        else SHG_LAUNCH_TMA(T, TXV, 3);                          \
+    } while (0)
+#define SHG_DISPATCH_TX(T)                                       \
+    do {                                                         \
+        if (TX == 256) SHG_DISPATCH_ST(T, 256);                  \
+        else if (TX == 128) SHG_DISPATCH_ST(T, 128);             \
+        else SHG_DISPATCH_ST(T, 64);                             \
+    } while (0)
+    if (bytes_per_px == 2) SHG_DISPATCH_TX(uint16_t);
+    else SHG_DISPATCH_TX(uint8_t);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,430 @@
+// Transversalium correction (reference solex_util.py:76-86, 383-395, 489-516).
+//
+// Stage 1 (shg_transv_row_stats): for every image row y inside the disk, over
+// the chord [xa, xb):   rat = log(img[y] / img[y-1])
+//                       out = mean(rat[|rat - median(rat)| / MAD < 2])
+// One CTA per row.  rat lives in shared memory (or an L2-resident scratch row
+// for very long chords); the two medians are exact order statistics found by a
+// fixed-point radix select (5 bits per level over a monotone 30-bit rescaling
+// of the value range, all-pairs ranking of the last <= 256 candidates).
+// log() comes from a 65536-entry fp64 table: pixels are uint16, so
+// log(a/b) = T[a] - T[b] to ~2e-15 absolute (the reference's own log is only
+// good to ~1e-16 relative of a value that is ~1e-2).
+// Stage 2 (shg_row_scale_u16): out = trunc(min(img * gain[row], 65535)).
+// Bound: HBM (each image is read once per stage, written once by stage 2).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = 1024;
+constexpr int kListCap = 256;
+constexpr double kQ = 1073741824.0;     // 2^30
+
+struct Shared {
+    unsigned int whist[32][33];
+    unsigned int hist[32];
+    double red[2][32];
+    double list[kListCap];
+    unsigned long long cnt[4];
+    int list_n;
+    int ibc[8];
+    double dbc[4];
+};
+
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// min and max over the block; result broadcast to every thread
+__device__ void block_minmax(double& mn, double& mx, Shared& S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __syncthreads();
+    if (lane == 0) { S.red[0][warp] = mn; S.red[1][warp] = mx; }
+    __syncthreads();
+    mn = warp_min(S.red[0][lane]);
+    mx = warp_max(S.red[1][lane]);
+}
+
+__device__ void block_sum2(double& a, double& b, Shared& S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { S.red[0][warp] = a; S.red[1][warp] = b; }
+    __syncthreads();
+    a = warp_sum(S.red[0][lane]);
+    b = warp_sum(S.red[1][lane]);
+}
+
+template <int KIND>
+__device__ __forceinline__ double key_of(const double* vals, int i, double med) {
+    const double v = vals[i];
+    return KIND == 0 ? v : fabs(v - med);
+}
+
+__device__ __forceinline__ uint32_t qkey(double x, double lo, double scale) {
+    double u = (x - lo) * scale;                       // monotone in x
+    u = fmin(fmax(u, 0.0), kQ - 1.0);
+    return double_floor_to_u32(u);
+}
+
+// Exact order statistics t (and t+1 when need2) of the keys that lie in the
+// finite range [lo, hi]; m = number of such keys; 0 <= t (< t+1) < m.
+// Results in S.dbc[0], S.dbc[1].
+template <int KIND>
+__device__ void block_select(const double* vals, int n, double med, double lo, double hi, int m, int t, bool need2,
+                             Shared& S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (!(hi > lo)) {                                    // all candidates equal
+            if (threadIdx.x == 0) { S.dbc[0] = lo; S.dbc[1] = lo; }
+            __syncthreads();
+            return;
+        }
+        double scale = kQ / (hi - lo);
+        if (!(scale < 1e300)) scale = 1e300;
+        uint32_t prefix = 0;
+        int level = 0;
+        for (; level < 6 && m > kListCap; ++level) {
+            const int pshift = 30 - 5 * level, bshift = 25 - 5 * level;
+            unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // 32 bins x 8-bit fields ... widened below
+            // per-thread counts can exceed 255 for very long rows: flush in chunks of 255 elements
+            unsigned int acc[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) acc[b] = 0;
+            int since = 0;
+            auto flush = [&]() {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    acc[b] += (unsigned int)((c0 >> (8 * b)) & 0xff);
+                    acc[8 + b] += (unsigned int)((c1 >> (8 * b)) & 0xff);
+                    acc[16 + b] += (unsigned int)((c2 >> (8 * b)) & 0xff);
+                    acc[24 + b] += (unsigned int)((c3 >> (8 * b)) & 0xff);
+                }
+                c0 = c1 = c2 = c3 = 0;
+                since = 0;
+            };
+            for (int i = threadIdx.x; i < n; i += kT) {
+                const double x = key_of<KIND>(vals, i, med);
+                if (x >= lo && x <= hi) {
+                    const uint32_t q = qkey(x, lo, scale);
+                    if ((q >> pshift) == prefix) {
+                        const uint32_t b = (q >> bshift) & 31u;
+                        const unsigned long long inc = 1ull << (8 * (b & 7u));
+                        const uint32_t g = b >> 3;
+                        c0 += g == 0 ? inc : 0ull;
+                        c1 += g == 1 ? inc : 0ull;
+                        c2 += g == 2 ? inc : 0ull;
+                        c3 += g == 3 ? inc : 0ull;
+                    }
+                }
+                if (++since == 255) flush();
+            }
+            flush();
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const unsigned int tot = __reduce_add_sync(0xffffffffu, acc[b]);
+                if (lane == b) S.whist[warp][b] = tot;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned int h = 0;
+                for (int w = 0; w < kT / 32; ++w) h += S.whist[w][lane];
+                // inclusive prefix over bins
+                unsigned int inc = h;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const unsigned int exc = inc - h;
+                if (h > 0 && (unsigned)t >= exc && (unsigned)t < inc) { S.ibc[0] = lane; S.ibc[1] = (int)exc; S.ibc[2] = (int)h; }
+                if (need2 && h > 0 && (unsigned)(t + 1) >= exc && (unsigned)(t + 1) < inc) S.ibc[3] = lane;
+            }
+            __syncthreads();
+            const int b0 = S.ibc[0], below = S.ibc[1], cnt = S.ibc[2];
+            const int b1 = need2 ? S.ibc[3] : b0;
+            __syncthreads();
+            if (b1 != b0) {
+                // ranks t and t+1 straddle two bins: max of bin b0, min of bin b1
+                double v0 = -INFINITY, v1 = INFINITY;
+                for (int i = threadIdx.x; i < n; i += kT) {
+                    const double x = key_of<KIND>(vals, i, med);
+                    if (x >= lo && x <= hi) {
+                        const uint32_t q = qkey(x, lo, scale);
+                        if ((q >> pshift) == prefix) {
+                            const int b = (int)((q >> bshift) & 31u);
+                            if (b == b0) v0 = fmax(v0, x);
+                            if (b == b1) v1 = fmin(v1, x);
+                        }
+                    }
+                }
+                block_minmax(v1, v0, S);
+                if (threadIdx.x == 0) { S.dbc[0] = v0; S.dbc[1] = v1; }
+                __syncthreads();
+                return;
+            }
+            t -= below;
+            m = cnt;
+            prefix = (prefix << 5) | (uint32_t)b0;
+        }
+        const int pshift = 30 - 5 * level;
+        if (m <= kListCap) {
+            if (threadIdx.x == 0) S.list_n = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += kT) {
+                const double x = key_of<KIND>(vals, i, med);
+                if (x >= lo && x <= hi) {
+                    const uint32_t q = qkey(x, lo, scale);
+                    if (level == 0 || (q >> pshift) == prefix) {
+                        const int slot = atomicAdd(&S.list_n, 1);
+                        if (slot < kListCap) S.list[slot] = x;
+                    }
+                }
+            }
+            __syncthreads();
+            const int mm = min(S.list_n, kListCap);
+            if ((int)threadIdx.x < mm) {
+                const double c = S.list[threadIdx.x];
+                int rank = 0;
+                for (int i = 0; i < mm; ++i) {
+                    const double o = S.list[i];
+                    rank += (o < c || (o == c && i < (int)threadIdx.x)) ? 1 : 0;
+                }
+                if (rank == t) S.dbc[0] = c;
+                if (rank == t + 1) S.dbc[1] = c;
+            }
+            __syncthreads();
+            if (!need2 && threadIdx.x == 0) S.dbc[1] = S.dbc[0];
+            __syncthreads();
+            return;
+        }
+        // 30 bits used up and still many candidates in one cell: rebase on their true range
+        double cmin = INFINITY, cmax = -INFINITY;
+        for (int i = threadIdx.x; i < n; i += kT) {
+            const double x = key_of<KIND>(vals, i, med);
+            if (x >= lo && x <= hi) {
+                const uint32_t q = qkey(x, lo, scale);
+                if (q == prefix) { cmin = fmin(cmin, x); cmax = fmax(cmax, x); }
+            }
+        }
+        block_minmax(cmin, cmax, S);
+        lo = cmin;
+        hi = cmax;
+    }
+}
+
+// value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
+template <int KIND>
+__device__ void ranked_pair(const double* vals, int n, double med, double lo, double hi, int nneg, int nfin,
+                            int t0, int t1, double& v0, double& v1, Shared& S) {
+    auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
+    const int g0 = group(t0), g1 = group(t1);
+    if (g0 == 0 && g1 == 0) {
+        block_select<KIND>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
+        v0 = S.dbc[0];
+        v1 = S.dbc[1];
+        __syncthreads();
+        return;
+    }
+    if (g0 == 0) {
+        block_select<KIND>(vals, n, med, lo, hi, nfin, t0 - nneg, false, S);
+        v0 = S.dbc[0];
+        __syncthreads();
+    } else {
+        v0 = g0 < 0 ? -INFINITY : INFINITY;
+    }
+    if (g1 == 0) {
+        block_select<KIND>(vals, n, med, lo, hi, nfin, t1 - nneg, false, S);
+        v1 = S.dbc[0];
+        __syncthreads();
+    } else {
+        v1 = g1 < 0 ? -INFINITY : INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+transv_row_stats_kernel(const uint16_t* __restrict__ img, int cols, const int32_t* __restrict__ rows,
+                        const int32_t* __restrict__ xa_list, const int32_t* __restrict__ xb_list,
+                        const double* __restrict__ logtab, double* __restrict__ out,
+                        double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw);
+    double* vals = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    const int j = blockIdx.x;
+    const int y = rows[j], xa = xa_list[j], xb = xb_list[j];
+    const int n = xb - xa;
+    if (n <= 0) {                                   // np.mean of an empty slice
+        if (threadIdx.x == 0) out[j] = NAN;
+        return;
+    }
+    if (n > smem_cap) vals = gscratch + (int64_t)j * scratch_pitch;
+    const uint16_t* ry = img + (int64_t)y * cols + xa;
+    const uint16_t* rp = img + (int64_t)(y - 1) * cols + xa;
+
+    // ---- rat = log(img[y]/img[y-1]) -------------------------------------------
+    double fmn = INFINITY, fmx = -INFINITY;
+    unsigned int nnan = 0, nneg = 0, npos = 0;
+    for (int i = threadIdx.x; i < n; i += kT) {
+        const double r = logtab[ry[i]] - logtab[rp[i]];
+        vals[i] = r;
+        if (r != r) ++nnan;
+        else if (r == -INFINITY) ++nneg;
+        else if (r == INFINITY) ++npos;
+        else { fmn = fmin(fmn, r); fmx = fmax(fmx, r); }
+    }
+    if (threadIdx.x < 4) S.cnt[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        const unsigned int a = __reduce_add_sync(0xffffffffu, nnan);
+        const unsigned int b = __reduce_add_sync(0xffffffffu, nneg);
+        const unsigned int c = __reduce_add_sync(0xffffffffu, npos);
+        if ((threadIdx.x & 31) == 0) {
+            if (a) atomicAdd(&S.cnt[0], (unsigned long long)a);
+            if (b) atomicAdd(&S.cnt[1], (unsigned long long)b);
+            if (c) atomicAdd(&S.cnt[2], (unsigned long long)c);
+        }
+    }
+    block_minmax(fmn, fmx, S);                       // also orders the smem writes of vals[]
+    __syncthreads();
+    const int t_nan = (int)S.cnt[0], t_neg = (int)S.cnt[1], t_pos = (int)S.cnt[2];
+    const int nfin = n - t_neg - t_pos;
+    if (t_nan > 0) {                                 // np.median -> nan -> everything rejected -> mean([]) = nan
+        if (threadIdx.x == 0) out[j] = NAN;
+        return;
+    }
+    // ---- median (np.median: mean of the two middle values for even n) ---------
+    const int t0 = (n - 1) / 2, t1 = n / 2;
+    double a0, a1;
+    ranked_pair<0>(vals, n, 0.0, fmn, fmx, t_neg, nfin, t0, t1, a0, a1, S);
+    const double med = t0 == t1 ? a0 : (a0 + a1) / 2.0;
+    if (!(fabs(med) < INFINITY)) {                   // |rat - med| contains nan -> mean([]) = nan
+        if (threadIdx.x == 0) out[j] = NAN;
+        return;
+    }
+    // ---- MAD -------------------------------------------------------------------
+    const int ninf = t_neg + t_pos;
+    double dhi = nfin > 0 ? fmax(fabs(fmn - med), fabs(fmx - med)) : 0.0;
+    double b0, b1;
+    ranked_pair<1>(vals, n, med, 0.0, dhi, 0, n - ninf, t0, t1, b0, b1, S);
+    const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
+    // ---- mean of the inliers ---------------------------------------------------
+    double sum = 0.0, cnt = 0.0;
+    if (mdev != 0.0) {                               // (nan is truthy in the reference too, but cannot occur here)
+        for (int i = threadIdx.x; i < n; i += kT) {
+            const double r = vals[i];
+            const double s = fabs(r - med) / mdev;
+            if (s < 2.0) { sum += r; cnt += 1.0; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += kT) { sum += vals[i]; cnt += 1.0; }
+    }
+    block_sum2(sum, cnt, S);
+    if (threadIdx.x == 0) out[j] = sum / cnt;
+}
+
+__global__ void __launch_bounds__(256)
+log_table_kernel(double* __restrict__ tab) {
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v < 65536) tab[v] = v == 0 ? -INFINITY : log((double)v);
+}
+
+__global__ void __launch_bounds__(256)
+row_scale_kernel(const uint16_t* __restrict__ img, int rows, int cols, const double* __restrict__ gain,
+                 uint16_t* __restrict__ out) {
+    const int r = blockIdx.y;
+    const double g = gain[r];
+    const uint16_t* src = img + (int64_t)r * cols;
+    uint16_t* dst = out + (int64_t)r * cols;
+    auto one = [&](uint32_t v) -> uint32_t {
+        double p = __dmul_rn(u32_to_double(v), g);
+        p = p > 65535.0 ? 65535.0 : p;               // ret[ret > 65535] = 65535
+        p = p > 0.0 ? p : 0.0;
+        return double_floor_to_u32(p) & 0xffffu;
+    };
+    const bool vec = (cols % 8 == 0) && ((uintptr_t)img % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (vec) {
+        const int nv = cols / 8;
+        for (int v = blockIdx.x * 256 + threadIdx.x; v < nv; v += gridDim.x * 256) {
+            const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(src) + v);
+            uint4 o;
+            o.x = one(q.x & 0xffffu) | (one(q.x >> 16) << 16);
+            o.y = one(q.y & 0xffffu) | (one(q.y >> 16) << 16);
+            o.z = one(q.z & 0xffffu) | (one(q.z >> 16) << 16);
+            o.w = one(q.w & 0xffffu) | (one(q.w >> 16) << 16);
+            reinterpret_cast<uint4*>(dst)[v] = o;
+        }
+    } else {
+        for (int c = blockIdx.x * 256 + threadIdx.x; c < cols; c += gridDim.x * 256) dst[c] = (uint16_t)one(src[c]);
+    }
+}
+
+}  // namespace
+
+extern "C" int shg_log_table(double* d_tab65536, void* stream) {
+    log_table_kernel<<<256, 256, 0, as_stream(stream)>>>(d_tab65536);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len) {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    const int64_t cap = ((int64_t)optin - (int64_t)((sizeof(Shared) + 15) / 16 * 16)) / 8;
+    if (max_len <= cap) return 0;
+    return (int64_t)n_list * (((int64_t)max_len + 15) / 16 * 16) * 8;
+}
+
+extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, const int32_t* d_rows,
+                                    const int32_t* d_xa, const int32_t* d_xb, int n_list, int max_len,
+                                    const double* d_logtab, double* d_out, void* d_work, int64_t work_bytes,
+                                    void* stream) {
+    (void)rows;
+    if (n_list <= 0) return 0;
+    SHG_REQUIRE(max_len >= 0 && max_len <= cols, "shg_transv_row_stats: max_len %d out of range", max_len);
+    int dev = 0, optin = 0;
+    SHG_CHECK(cudaGetDevice(&dev));
+    SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int64_t head = (sizeof(Shared) + 15) / 16 * 16;
+    const int64_t cap = (optin - head) / 8;
+    int64_t pitch = 0;
+    size_t smem = (size_t)head;
+    if (max_len <= cap) {
+        smem += (size_t)max_len * 8;
+    } else {
+        pitch = ((int64_t)max_len + 15) / 16 * 16;
+        SHG_REQUIRE(d_work && work_bytes >= (int64_t)n_list * pitch * 8,
+                    "shg_transv_row_stats: chords of %d px need %lld bytes of workspace", max_len,
+                    (long long)((int64_t)n_list * pitch * 8));
+    }
+    SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transv_row_stats_kernel<<<n_list, kT, smem, as_stream(stream)>>>(
+        d_img, cols, d_rows, d_xa, d_xb, d_logtab, d_out, static_cast<double*>(d_work), pitch,
+        max_len <= cap ? max_len : 0);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, const double* d_gain, uint16_t* d_out,
+                                 void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    SHG_REQUIRE(rows <= 65535, "shg_row_scale_u16: too many rows");
+    const int per_row = std::max(1, std::min(8, (cols / 8 + 255) / 256));
+    row_scale_kernel<<<dim3(per_row, rows), 256, 0, as_stream(stream)>>>(d_img, rows, cols, d_gain, d_out);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,139 @@
+// Circularisation warp and the 4x4 downscale that feeds the ellipse fit.
+//
+// The reference warps with skimage.transform.warp(image, ProjectiveTransform(mat3),
+// order 1, constant mode) (ellipse_to_circle.py:94-118).  get_correction_matrix
+// (ellipse_to_circle.py:39-50) always yields mat3 rows 1,2 == [0,1,0],[0,0,1]:
+// every output row samples only its own input row, so the warp is a 1-D
+// linear resample along the frame axis:
+//     x = (m00*c + m01*r) + m02
+//     out[r][c] = trunc(clip((1-d)*in[r][floor x] + d*in[r][ceil x], lo, hi)),  d = x - floor x
+// with taps outside the image reading cval = image[0][0].  The disk arrives
+// frame-major (N, ih), so a CTA stages [frame span] x [64 slit rows] in shared
+// memory with coalesced loads and writes (ih, Wout) rows with coalesced stores:
+// the warp doubles as the transpose to the reference layout.
+// Bound: HBM, ih*N*2 bytes read + ih*Wout*2 bytes written per image.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRows = 64;      // slit rows per tile
+constexpr int kCols = 256;     // output columns per tile = threads
+constexpr int kPitch = kRows + 2;
+
+__global__ void __launch_bounds__(kCols)
+warp_rows_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, int flip,
+                 double m00, double m01, double m02, double cval, double lo, double hi,
+                 uint16_t* __restrict__ out, int out_rows, int out_cols, int span) {
+    extern __shared__ uint16_t tile[];           // [span][kPitch]
+    const int r0 = blockIdx.y * kRows;
+    const int c0 = blockIdx.x * kCols;
+    const int r1 = min(r0 + kRows, out_rows);
+    const int c1 = min(c0 + kCols, out_cols);
+    // frame range touched by this tile (x is monotone in c and in r)
+    double xa = 1e300, xb = -1e300;
+    {
+        const double cs[2] = {(double)c0, (double)(c1 - 1)};
+        const double rs[2] = {(double)r0, (double)(r1 - 1)};
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const double x = __dadd_rn(__dadd_rn(__dmul_rn(m00, cs[a]), __dmul_rn(m01, rs[b])), m02);
+                xa = fmin(xa, x);
+                xb = fmax(xb, x);
+            }
+    }
+    // clamp before converting: far outside the image everything is cval anyway
+    xa = fmax(xa, -4.0);
+    xb = fmin(xb, (double)n_frames + 4.0);
+    const int64_t kbase = (int64_t)floor(xa);
+    const int64_t kend = min((int64_t)ceil(xb) + 1, kbase + span);   // exclusive
+    const int nrow = min(r1, ih) - r0;                                // valid slit rows (may be <= 0)
+    // ---- stage: coalesced along the slit axis --------------------------------
+    for (int64_t kk = kbase + (threadIdx.x >> 5); kk < kend; kk += kCols / 32) {
+        uint16_t* dst = tile + (kk - kbase) * kPitch;
+        if (kk < 0 || kk >= n_frames) continue;                        // never read (range test below)
+        const int64_t ksrc = flip ? (n_frames - 1 - kk) : kk;
+        const uint16_t* src = disk + ksrc * ih + r0;
+        for (int j = (threadIdx.x & 31) * 2; j < nrow; j += 64) {
+            if (j + 1 < nrow && (((uintptr_t)(src + j)) & 3) == 0) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + j);
+                *reinterpret_cast<uint32_t*>(dst + j) = v;
+            } else {
+                dst[j] = src[j];
+                if (j + 1 < nrow) dst[j + 1] = src[j + 1];
+            }
+        }
+    }
+    __syncthreads();
+    const int c = c0 + threadIdx.x;
+    if (c >= out_cols) return;
+    const double mc = __dmul_rn(m00, (double)c);
+    for (int r = r0; r < r1; ++r) {
+        const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
+        const double xf = floor(x), xc = ceil(x);
+        const double d = __dsub_rn(x, xf);
+        double L = cval, R = cval;
+        if (r < ih) {
+            if (xf >= 0.0 && xf < (double)n_frames) L = u32_to_double(tile[((int64_t)xf - kbase) * kPitch + (r - r0)]);
+            if (xc >= 0.0 && xc < (double)n_frames) R = u32_to_double(tile[((int64_t)xc - kbase) * kPitch + (r - r0)]);
+        }
+        double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
+        v = fmin(fmax(v, lo), hi);
+        out[(int64_t)r * out_cols + c] = (uint16_t)double_floor_to_u32(v);
+    }
+}
+
+// out[ri][ci] = sum over the 4x4 block of image[r][k] = disk[k][r] (zero padded)
+__global__ void __launch_bounds__(256)
+downscale4_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, int flip,
+                  uint32_t* __restrict__ out, int out_rows, int out_cols) {
+    // thread -> (ci, ri) with ri fastest so the 4 slit rows of one frame are one 8-byte run
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)out_rows * out_cols) return;
+    const int ri = (int)(idx % out_rows);
+    const int64_t ci = idx / out_rows;
+    uint32_t s = 0;
+    for (int dk = 0; dk < 4; ++dk) {
+        const int64_t k = ci * 4 + dk;
+        if (k >= n_frames) break;
+        const uint16_t* p = disk + (flip ? (n_frames - 1 - k) : k) * ih + ri * 4;
+        for (int dr = 0; dr < 4; ++dr)
+            if (ri * 4 + dr < ih) s += p[dr];
+    }
+    out[(int64_t)ri * out_cols + ci] = s;
+}
+
+}  // namespace
+
+extern "C" int shg_warp_rows(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
+                             double m00, double m01, double m02, double cval, double lo, double hi,
+                             uint16_t* d_out, int out_rows, int out_cols, void* stream) {
+    SHG_REQUIRE(n_frames > 0 && ih > 0 && out_rows > 0 && out_cols > 0, "shg_warp_rows: bad geometry");
+    SHG_REQUIRE(std::isfinite(m00) && std::isfinite(m01) && std::isfinite(m02) && m00 > 0.0,
+                "shg_warp_rows: bad matrix (%g, %g, %g)", m00, m01, m02);
+    // frames spanned by one tile: kCols columns and kRows rows, + floor/ceil taps
+    const double spanf = m00 * (kCols - 1) + std::fabs(m01) * (kRows - 1) + 4.0;
+    SHG_REQUIRE(spanf < 1500.0, "shg_warp_rows: stretch %g / shear %g too large for the tile", m00, m01);
+    const int span = (int)std::ceil(spanf);
+    const size_t smem = (size_t)span * kPitch * sizeof(uint16_t);
+    SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((out_cols + kCols - 1) / kCols, (out_rows + kRows - 1) / kRows);
+    SHG_REQUIRE(grid.y <= 65535, "shg_warp_rows: too many rows");
+    warp_rows_kernel<<<grid, kCols, smem, as_stream(stream)>>>(d_disk, n_frames, ih, flip, m00, m01, m02, cval, lo, hi,
+                                                             d_out, out_rows, out_cols, span);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_downscale4_sum(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
+                                  uint32_t* d_out, int out_rows, int out_cols, void* stream) {
+    SHG_REQUIRE(out_rows == (ih + 3) / 4 && out_cols == (int)((n_frames + 3) / 4),
+                "shg_downscale4_sum: output must be ceil(ih/4) x ceil(N/4)");
+    const int64_t n = (int64_t)out_rows * out_cols;
+    downscale4_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(d_disk, n_frames, ih, flip, d_out,
+                                                                                  out_rows, out_cols);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,407 @@
+"""Host side of the B200 reconstruction path: device buffers (torch tensors used
+purely as memory), streams, and one method per stage of the reference's path,
+each a thin call into libshg.so through ctypes.
+
+Stage map (reference file:line -> method):
+  video_reader.py:94-123 + solex_util.py:174-188   ingest_file / ingest_array / accumulate
+  solex_util.py:188                                 finalize_mean_max
+  solex_util.py:165-172,223-231,242                 detect_line
+  solex_util.py:233-259                             fit_line
+  solex_util.py:93-144                              recon
+  ellipse_to_circle.py:94-145                       warp
+  solex_util.py:383-516                             transversalium
+
+There is no CPU fallback anywhere in this module: it needs libshg.so and a
+CUDA device, and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ShgError, call, lib
+
+
+@dataclass(frozen=True)
+class ScanGeometry:
+    """Raw-file geometry of a scan (video_reader.py:31-91)."""
+    width: int
+    height: int
+    bytes_per_px: int          # 1 (8-bit, scaled by 256 on use) or 2
+    n_frames: int              # frames of the whole scan
+
+    @property
+    def rotated(self):
+        return self.width > self.height
+
+    @property
+    def ih(self):
+        return self.width if self.rotated else self.height
+
+    @property
+    def iw(self):
+        return self.height if self.rotated else self.width
+
+    @property
+    def frame_px(self):
+        return self.width * self.height
+
+    @property
+    def frame_bytes(self):
+        return self.frame_px * self.bytes_per_px
+
+
+class DeviceStack:
+    """Frames [k0, k0+n) of a scan, resident in HBM in raw file layout, with
+    the running integer sum / max of those frames."""
+
+    def __init__(self, geom: ScanGeometry, k0: int, n: int, device):
+        self.geom, self.k0, self.n = geom, int(k0), int(n)
+        self.frames = torch.empty(max(1, self.n * geom.frame_bytes), dtype=torch.uint8, device=device)
+        self.sum = torch.zeros(geom.frame_px, dtype=torch.int64, device=device)      # uint64 bit pattern
+        self.max = torch.zeros(geom.frame_px, dtype=torch.int32, device=device)      # uint32 bit pattern
+        self.accumulated = False
+
+    def frame_ptr(self, k_local: int) -> int:
+        return self.frames.data_ptr() + k_local * self.geom.frame_bytes
+
+    def host_frames(self, k_local0: int, k_local1: int) -> np.ndarray:
+        """Raw frames copied back to the host as (n, H, W) -- tests only."""
+        g = self.geom
+        a = self.frames[k_local0 * g.frame_bytes:k_local1 * g.frame_bytes].cpu().numpy()
+        return a.view(np.uint8 if g.bytes_per_px == 1 else np.uint16).reshape(-1, g.height, g.width)
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Engine:
+    """One per process / GPU."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise ShgError('no CUDA device: the reconstruction path has no CPU fallback')
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', os.environ.get('SHG_DEVICE', '0')))
+        self.index = int(device)
+        self.device = torch.device('cuda', self.index)
+        torch.cuda.set_device(self.device)
+        info = (C.c_int64 * 6)()
+        call('shg_device_info', self.index, info)
+        self.sm_count, self.cc = int(info[0]), (int(info[1]), int(info[2]))
+        self.hbm_bytes, self.l2_bytes, self.smem_optin = int(info[3]), int(info[4]), int(info[5])
+        self._logtab = None
+        self._ingest = None
+        self._ingest_cfg = None
+        self.n_launches = 0            # kernels launched through this engine (bench's gpu_launches)
+
+    # ------------------------------------------------------------------ util
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    # ---------------------------------------------------------------- ingest
+    def _ring(self, slot_bytes, n_slots, n_threads):
+        cfg = (int(slot_bytes), int(n_slots), int(n_threads))
+        if self._ingest is not None and self._ingest_cfg == cfg:
+            return self._ingest
+        self.close_ring()
+        h = C.c_void_p()
+        call('shg_ingest_create', self.index, cfg[0], cfg[1], cfg[2], C.byref(h))
+        self._ingest, self._ingest_cfg = h, cfg
+        return h
+
+    def close_ring(self):
+        if self._ingest is not None:
+            lib.shg_ingest_destroy(self._ingest)
+            self._ingest = None
+
+    def __del__(self):
+        try:
+            self.close_ring()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _slot_bytes(geom, slot_mb):
+        per = max(1, (slot_mb << 20) // geom.frame_bytes)
+        return per * geom.frame_bytes
+
+    def ingest_file(self, path: str, geom: ScanGeometry, payload_offset: int, frame_stride: int | None = None,
+                    k0: int = 0, n: int | None = None, accumulate: bool = True, slot_mb: int = 64,
+                    n_slots: int = 4, n_threads: int = 8, stack: DeviceStack | None = None):
+        """File -> pinned ring -> HBM, mean/max accumulation overlapped.
+        Returns (stack, stats) with stats = (seconds, seconds reading, bytes, chunks)."""
+        n = geom.n_frames - k0 if n is None else n
+        if stack is None:
+            stack = DeviceStack(geom, k0, n, self.device)
+        ring = self._ring(self._slot_bytes(geom, slot_mb), n_slots, n_threads)
+        stats = (C.c_double * 4)()
+        torch.cuda.current_stream(self.device).synchronize()        # zero-fill of sum/max must be done
+        call('shg_ingest_file', ring, os.fsencode(path), int(payload_offset), geom.frame_bytes,
+             int(frame_stride or geom.frame_bytes), int(k0), int(n), stack.frames.data_ptr(), geom.bytes_per_px,
+             _ptr(stack.sum) if accumulate else 0, _ptr(stack.max) if accumulate else 0, stats)
+        stack.accumulated = bool(accumulate)
+        self.n_launches += int(stats[3]) if accumulate else 0
+        return stack, tuple(stats)
+
+    def ingest_host(self, host_ptr: int, geom: ScanGeometry, n: int, k0: int = 0, frame_stride: int | None = None,
+                    accumulate: bool = True, slot_mb: int = 256, n_slots: int = 4, n_threads: int = 8,
+                    stack: DeviceStack | None = None):
+        """Host memory image of the payload (mmap, pinned buffer, ndarray) -> HBM."""
+        if stack is None:
+            stack = DeviceStack(geom, k0, n, self.device)
+        ring = self._ring(self._slot_bytes(geom, slot_mb), n_slots, n_threads)
+        stats = (C.c_double * 4)()
+        torch.cuda.current_stream(self.device).synchronize()
+        call('shg_ingest_memory', ring, int(host_ptr), geom.frame_bytes, int(frame_stride or geom.frame_bytes),
+             int(n), stack.frames.data_ptr(), geom.bytes_per_px,
+             _ptr(stack.sum) if accumulate else 0, _ptr(stack.max) if accumulate else 0, stats)
+        stack.accumulated = bool(accumulate)
+        self.n_launches += int(stats[3]) if accumulate else 0
+        return stack, tuple(stats)
+
+    def ingest_array(self, frames: np.ndarray, n_total: int | None = None, k0: int = 0, accumulate: bool = True):
+        """(N, H, W) uint8/uint16 ndarray -> stack."""
+        frames = np.ascontiguousarray(frames)
+        n, h, w = frames.shape
+        geom = ScanGeometry(w, h, frames.dtype.itemsize, n if n_total is None else n_total)
+        stack, _ = self.ingest_host(frames.ctypes.data, geom, n, k0=k0, accumulate=accumulate, slot_mb=16)
+        return stack
+
+    def synth_stack(self, geom: ScanGeometry, k0: int = 0, n: int | None = None, seed: int = 1) -> DeviceStack:
+        n = geom.n_frames - k0 if n is None else n
+        stack = DeviceStack(geom, k0, n, self.device)
+        call('shg_synth_fill', stack.frames.data_ptr(), geom.bytes_per_px, k0, n, geom.n_frames, geom.width,
+             geom.height, seed, self.stream)
+        return stack
+
+    # ------------------------------------------------------- pass 1: mean/max
+    def accumulate(self, stack: DeviceStack, reset: bool = True):
+        if reset:
+            stack.sum.zero_()
+            stack.max.zero_()
+        g = stack.geom
+        call('shg_accumulate', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.frame_px,
+             stack.sum.data_ptr(), stack.max.data_ptr(), self.stream)
+        self.n_launches += 1
+        stack.accumulated = True
+
+    def finalize_mean_max(self, sum_t, max_t, n_total: int, geom: ScanGeometry):
+        mean_img = self.empty((geom.ih, geom.iw), torch.uint16)
+        max_img = self.empty((geom.ih, geom.iw), torch.uint16)
+        call('shg_finalize_mean_max', sum_t.data_ptr(), max_t.data_ptr(), int(n_total), geom.width, geom.height,
+             1 if geom.bytes_per_px == 1 else 0, mean_img.data_ptr(), max_img.data_ptr(), self.stream)
+        self.n_launches += 1
+        return mean_img, max_img
+
+    # ------------------------------------------------- line detection and fit
+    def box_blur(self, img, kw: int, kh: int):
+        rows, cols = img.shape
+        out = self.empty((rows, cols), torch.uint16)
+        tmp = self.empty((rows, cols), torch.int32)
+        call('shg_box_blur_u16', img.data_ptr(), rows, cols, int(kw), int(kh), out.data_ptr(), tmp.data_ptr(),
+             self.stream)
+        self.n_launches += 2
+        return out
+
+    def detect_line(self, mean_img, max_img):
+        """Slit extent from the max frame and the blurred / sharp per-row minima of
+        the mean frame (solex_util.py:165-172, 223-231, 242)."""
+        ih, iw = mean_img.shape
+        blur5 = self.box_blur(max_img, 5, 5)
+        sums = self.empty((ih,), torch.int64)
+        call('shg_row_sums_u16', blur5.data_ptr(), ih, iw, sums.data_ptr(), self.stream)
+        self.n_launches += 1
+        ymean = sums.cpu().numpy().astype(np.float64) / iw                # np.mean(blur, axis=1): exact sums
+        where_sun = ymean > np.median(ymean) / 5
+        lb = int(np.argmax(where_sun))
+        ub = int(ih - 1 - np.argmax(where_sun[::-1]))
+        clip = int((ub - lb) * 0.05)
+        y1 = min(ih - 1, lb + clip)
+        y2 = max(0, ub - clip)
+        bwy = int((y2 - y1) * 0.01)
+        blur = self.box_blur(mean_img, 25, bwy)                           # raises for bwy < 1 like cv2.blur
+        mi = self.empty((ih,), torch.int32)
+        ms = self.empty((ih,), torch.int32)
+        if iw - 13 <= 12:
+            raise ShgError('frames are too narrow along the dispersion axis (%d px) for the 25 px blur window' % iw)
+        call('shg_row_argmin_u16', blur.data_ptr(), ih, iw, 12, iw - 13, mi.data_ptr(), self.stream)
+        call('shg_row_argmin_u16', mean_img.data_ptr(), ih, iw, 0, iw, ms.data_ptr(), self.stream)
+        self.n_launches += 2
+        return dict(y1=y1, y2=y2, min_intensity=mi, min_sharp=ms)
+
+    def fit_line(self, det, ih: int):
+        """The three cubic fits with their outlier logic (solex_util.py:233-259).
+        Moment sums, residuals and masks on the device; the O(ih) mode-of-tenths
+        bookkeeping calls NumPy exactly as the reference does."""
+        y1, y2 = det['y1'], det['y2']
+        n = y2 - y1
+        if n < 4:
+            raise ShgError('spectral line fit needs at least 4 slit rows, got %d (y1=%d, y2=%d)' % (n, y1, y2))
+        mi, ms = det['min_intensity'][y1:y2], det['min_sharp'][y1:y2]
+        coef = self.empty((3, 4), torch.float64)
+        resid = self.empty((n,), torch.float64)
+        keep = self.empty((n,), torch.uint8)
+        good = self.empty((n,), torch.uint8)
+        st = self.stream
+        call('shg_polyfit3', mi.data_ptr(), 0, y1, n, coef[0].data_ptr(), mi.data_ptr(), resid.data_ptr(), st)
+        call('shg_sigma_mask', resid.data_ptr(), n, 3.0, keep.data_ptr(), st)
+        call('shg_polyfit3', mi.data_ptr(), keep.data_ptr(), y1, n, coef[1].data_ptr(), ms.data_ptr(),
+             resid.data_ptr(), st)
+        self.n_launches += 3
+        delta_sharp = resid.cpu().numpy()
+        values, counts = np.unique(np.around(delta_sharp, 1), return_counts=True)
+        ind = np.argpartition(-counts, kth=2)[:2]                         # ValueError for < 3 bins, as upstream
+        shift = float(values[ind[0]])
+        call('shg_window_mask', resid.data_ptr(), n, shift, 5.0, good.data_ptr(), st)
+        call('shg_polyfit3', ms.data_ptr(), good.data_ptr(), y1, n, coef[2].data_ptr(), 0, 0, st)
+        fit = self.empty((ih, 4), torch.float64)
+        call('shg_fit_table', coef[2].data_ptr(), ih, fit.data_ptr(), st)
+        self.n_launches += 3
+        coef_h = coef.cpu().numpy()
+        return dict(p1=coef_h[0], p2=coef_h[1], p3=coef_h[2], shift=shift, fit=fit.cpu().numpy(),
+                    keep=keep, mask_good=good)
+
+    # ------------------------------------------------------- pass 2: recon
+    def alloc_disk(self, n_shifts: int, n_frames: int, ih: int):
+        return self.empty((n_shifts, n_frames, ih), torch.uint16)
+
+    def recon(self, stack: DeviceStack, fit: np.ndarray, shifts, disk=None, k0_out: int | None = None,
+              impl: int = 0):
+        """disk[s, k, i] (frame-major) for the frames of `stack`; with `disk`
+        given the rows land at frame offset k0_out (default: the stack's k0)."""
+        g = stack.geom
+        shifts = np.ascontiguousarray(shifts, dtype=np.int32)
+        fit = np.ascontiguousarray(fit, dtype=np.float64)
+        assert fit.shape == (g.ih, 4)
+        if disk is None:
+            disk = self.alloc_disk(len(shifts), stack.n, g.ih)
+            k0_out = 0
+        elif k0_out is None:
+            k0_out = stack.k0
+        assert disk.shape[0] == len(shifts) and disk.shape[2] == g.ih and disk.is_contiguous()
+        wb = int(lib.shg_recon_workspace_bytes(g.ih, len(shifts)))
+        if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
+            self._recon_ws = self.empty((wb,), torch.uint8)
+        call('shg_recon', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.width, g.height,
+             fit.ctypes.data, shifts.ctypes.data, len(shifts), disk.data_ptr(), disk.stride(0), int(k0_out),
+             int(impl), self._recon_ws.data_ptr(), wb, self.stream)
+        self.n_launches += 1
+        return disk
+
+    def to_reference_layout(self, disk_s, flip: bool = False):
+        """(N, ih) frame-major -> the reference's (ih, N) image; flip = np.flip(axis=1)."""
+        n, ih = disk_s.shape
+        out = self.empty((ih, n), torch.uint16)
+        call('shg_transpose_u16', disk_s.data_ptr(), n, ih, out.data_ptr(), 1 if flip else 0, self.stream)
+        self.n_launches += 1
+        return out
+
+    def minmax(self, img):
+        mm = torch.tensor([65535, 0], dtype=torch.int32, device=self.device)
+        call('shg_minmax_u16', img.data_ptr(), img.numel(), mm.data_ptr(), self.stream)
+        self.n_launches += 1
+        lo, hi = mm.cpu().tolist()
+        return int(lo), int(hi)
+
+    # -------------------------------------------------- circularisation warp
+    def warp(self, disk_s, flip: bool, mat3: np.ndarray, out_shape, cval: float, lo: float, hi: float, out=None):
+        """correct_image's pixel work (ellipse_to_circle.py:112-118) on a
+        frame-major disk; returns the (ih', Wout) uint16 image."""
+        n, ih = disk_s.shape
+        if not (mat3[1, 0] == 0 and mat3[1, 1] == 1 and mat3[1, 2] == 0 and
+                mat3[2, 0] == 0 and mat3[2, 1] == 0 and mat3[2, 2] == 1):
+            raise ShgError('warp matrix is not the row-preserving form get_correction_matrix produces')
+        oh, ow = int(out_shape[0]), int(out_shape[1])
+        if out is None:
+            out = self.empty((oh, ow), torch.uint16)
+        call('shg_warp_rows', disk_s.data_ptr(), n, ih, 1 if flip else 0, float(mat3[0, 0]), float(mat3[0, 1]),
+             float(mat3[0, 2]), float(cval), float(lo), float(hi), out.data_ptr(), oh, ow, self.stream)
+        self.n_launches += 1
+        return out
+
+    def downscale4(self, disk_s, flip: bool):
+        """4x4 block sums of the (ih, N) image (ellipse_to_circle.py:301)."""
+        n, ih = disk_s.shape
+        out = self.empty(((ih + 3) // 4, (n + 3) // 4), torch.int32)
+        call('shg_downscale4_sum', disk_s.data_ptr(), n, ih, 1 if flip else 0, out.data_ptr(), out.shape[0],
+             out.shape[1], self.stream)
+        self.n_launches += 1
+        return out
+
+    # ------------------------------------------------------- transversalium
+    @property
+    def logtab(self):
+        if self._logtab is None:
+            self._logtab = self.empty((65536,), torch.float64)
+            call('shg_log_table', self._logtab.data_ptr(), self.stream)
+        return self._logtab
+
+    @staticmethod
+    def transversalium_chords(circle, borders):
+        """Row range and per-row chord of correct_transversalium2 (solex_util.py:384-391)."""
+        cx, cy, rad = circle
+        y1 = math.ceil(max(cy - rad, borders[1]))
+        y2 = math.floor(min(cy + rad, borders[3]))
+        rows, xa, xb = [], [], []
+        for y in range(y1 + 1, y2):
+            dx = math.floor((rad ** 2 - (y - cy) ** 2) ** 0.5)
+            rows.append(y)
+            xa.append(math.ceil(max(cx - dx, borders[0])))
+            xb.append(math.floor(min(cx + dx, borders[2])))
+        return y1, y2, np.asarray(rows, np.int32), np.asarray(xa, np.int32), np.asarray(xb, np.int32)
+
+    def transversalium_row_stats(self, img, rows, xa, xb):
+        """Per-row robust mean of log(img[y]/img[y-1]) over [xa, xb) (solex_util.py:392-395)."""
+        n = len(rows)
+        if n == 0:
+            return np.zeros(0)
+        h, w = img.shape
+        if rows.min() < 1 or rows.max() >= h or xa.min() < 0 or xb.max() > w:
+            raise IndexError('transversalium chord outside the image')     # the reference would raise / wrap too
+        idx = torch.from_numpy(np.stack([rows, xa, xb])).to(self.device)
+        out = self.empty((n,), torch.float64)
+        max_len = int(max(0, (xb - xa).max()))
+        wb = int(lib.shg_transv_workspace_bytes(n, max_len))
+        work = self.empty((wb,), torch.uint8) if wb > 0 else None
+        call('shg_transv_row_stats', img.data_ptr(), h, w, idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(),
+             n, max_len, self.logtab.data_ptr(), out.data_ptr(), _ptr(work), wb, self.stream)
+        self.n_launches += 1
+        return out.cpu().numpy()
+
+    def row_scale(self, img, gain: np.ndarray, out=None):
+        """(img.T * c).T, clip 65535, truncate (solex_util.py:489,515-516)."""
+        h, w = img.shape
+        g = torch.from_numpy(np.ascontiguousarray(gain, dtype=np.float64)).to(self.device)
+        if out is None:
+            out = self.empty((h, w), torch.uint16)
+        call('shg_row_scale_u16', img.data_ptr(), h, w, g.data_ptr(), out.data_ptr(), self.stream)
+        self.n_launches += 1
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine for a device (created on first use; never in a forked child)."""
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', os.environ.get('SHG_DEVICE', '0')))
+    key = (os.getpid(), int(device))
+    if key not in _engines:
+        _engines[key] = Engine(device)
+    return _engines[key]

@@ -1,0 +1,43 @@
+"""CPU: the C-ABI library loads and exports every symbol include/shg.h declares
+(no compute calls -- those need a GPU)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'shg.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(shg_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from solex_ser_recon_en_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(_lib.lib, n), n
+    assert sorted(_lib.EXPORTS) == names, 'ctypes prototypes and shg.h disagree'
+    assert _lib.lib.shg_version() == 1
+    assert _lib.lib.shg_last_error() == b''
+
+
+def test_every_declaration_cites_the_reference():
+    src = open(os.path.join(ROOT, 'include', 'shg.h')).read()
+    for ref in ('solex_util.py:174-188', 'solex_util.py:93-144', 'ellipse_to_circle.py:94-118',
+                'video_reader.py:94-123', 'solex_util.py:233-259', 'solex_util.py:76-86'):
+        assert ref in src, ref
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from solex_ser_recon_en_b200.engine import Engine
+    from solex_ser_recon_en_b200._lib import ShgError
+    with pytest.raises(ShgError):
+        Engine(0)

@@ -1,0 +1,419 @@
+"""GPU parity tests: every libshg entry point (called through the ctypes C ABI
+via solex_ser_recon_en_b200.engine) against the oracle and against the golden
+fixtures recorded from the unmodified reference.  Integer / index results must
+be bit-exact; coefficients within 1e-6 relative; images within 1 DN (in
+practice they are bit-exact too, and the tests say so where that holds)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import shg_oracle as O
+from oracle.make_golden import CASES
+from helpers import ALL_CASES, case_file, case_stack, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from solex_ser_recon_en_b200.engine import get_engine
+    return get_engine(0)
+
+
+def u16(t):
+    return t.cpu().numpy()
+
+
+def stack_stats(eng, stack):
+    st = eng.ingest_array(stack)
+    mean_img, max_img = eng.finalize_mean_max(st.sum, st.max, st.n, st.geom)
+    return st, mean_img, max_img
+
+
+# ------------------------------------------------------------------ pass 1
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_mean_max_bit_exact(eng, name):
+    g = golden(name)
+    _, stack = case_stack(name)
+    st, mean_img, max_img = stack_stats(eng, stack)
+    s_ref, m_ref = O.raw_sum_max(stack)
+    assert np.array_equal(st.sum.cpu().numpy().view(np.uint64).reshape(s_ref.shape), s_ref)
+    assert np.array_equal(st.max.cpu().numpy().reshape(m_ref.shape), m_ref.astype(np.int32))
+    assert np.array_equal(u16(mean_img), g['mean_img'])
+    assert np.array_equal(u16(max_img), g['max_img'])
+
+
+@pytest.mark.parametrize('shape', [(37, 5, 7), (3, 17, 33), (130, 24, 40), (1, 8, 8), (70, 31, 64)])
+@pytest.mark.parametrize('dtype', [np.uint8, np.uint16])
+def test_accumulate_ragged_geometries(eng, shape, dtype):
+    """Frame sizes that are / are not multiples of 16 bytes, extreme values."""
+    rng = np.random.default_rng(sum(shape))
+    top = 255 if dtype == np.uint8 else 65535
+    stack = rng.integers(0, top + 1, size=shape).astype(dtype)
+    stack[0, 0, 0] = top
+    stack[:, -1, -1] = top
+    st = eng.ingest_array(stack)
+    s_ref, m_ref = O.raw_sum_max(stack)
+    assert np.array_equal(st.sum.cpu().numpy().view(np.uint64).reshape(s_ref.shape), s_ref)
+    assert np.array_equal(st.max.cpu().numpy().reshape(m_ref.shape), m_ref.astype(np.int32))
+    mean_img, max_img = eng.finalize_mean_max(st.sum, st.max, st.n, st.geom)
+    mo, xo = O.finalize_mean_max(s_ref, m_ref, shape[0], dtype == np.uint8)
+    assert np.array_equal(u16(mean_img), mo) and np.array_equal(u16(max_img), xo)
+
+
+def test_accumulate_partial_ranges_add_exactly(eng):
+    """What ranks all-reduce: sums / maxima of frame ranges combine exactly."""
+    _, stack = case_stack('ser16_rot')
+    a = eng.ingest_array(stack[:77], n_total=stack.shape[0])
+    b = eng.ingest_array(stack[77:], n_total=stack.shape[0], k0=77)
+    full = eng.ingest_array(stack)
+    assert np.array_equal((a.sum + b.sum).cpu().numpy(), full.sum.cpu().numpy())
+    import torch
+    assert np.array_equal(torch.maximum(a.max, b.max).cpu().numpy(), full.max.cpu().numpy())
+
+
+# --------------------------------------------------------------- detection
+def test_box_blur_matches_cv2(eng):
+    import cv2
+    import torch
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        H = int(rng.integers(60, 300)); W = int(rng.integers(40, 260))
+        kh = int(rng.integers(1, 40)); kw = 25 if trial % 3 else int(rng.integers(1, 30))
+        if trial % 5 == 0:
+            kw, kh = 5, 5
+        hi = [65535, 4000, 300][trial % 3]
+        img = rng.integers(0, hi + 1, size=(H, W)).astype(np.uint16)
+        out = eng.box_blur(torch.from_numpy(img).to(eng.device), kw, kh)
+        assert np.array_equal(u16(out), cv2.blur(img, ksize=(kw, kh))), (H, W, kw, kh)
+
+
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_detection_and_fit(eng, name):
+    g = golden(name)
+    _, stack = case_stack(name)
+    st, mean_img, max_img = stack_stats(eng, stack)
+    det = eng.detect_line(mean_img, max_img)
+    y1, y2 = det['y1'], det['y2']
+    assert (y1, y2) == (int(g['y1']), int(g['y2']))
+    mi = det['min_intensity'].cpu().numpy()
+    ms = det['min_sharp'].cpu().numpy()
+    assert np.array_equal(mi[y1:y2], g['polyfit0_y'])                 # integer line indices: bit-exact
+    assert np.array_equal(ms, g['min_sharp'])
+    lf = eng.fit_line(det, st.geom.ih)
+    keep = lf['keep'].cpu().numpy().astype(bool)
+    good = lf['mask_good'].cpu().numpy().astype(bool)
+    assert np.array_equal(mi[y1:y2][keep], g['polyfit1_y'])
+    assert np.array_equal(ms[y1:y2][good], g['polyfit2_y'])
+    for k, key in enumerate(('p1', 'p2', 'p3')):
+        np.testing.assert_allclose(lf[key], g[f'polyfit{k}_p'], rtol=1e-6, atol=0)
+    assert np.array_equal(lf['fit'][:, 0], g['fit'][:, 0])
+    np.testing.assert_allclose(lf['fit'], g['fit'], rtol=0, atol=1e-7)
+
+
+def test_polyfit_against_numpy(eng):
+    import torch
+    rng = np.random.default_rng(5)
+    for n, x0 in ((200, 0), (1000, 137), (4000, 48), (7, 3), (4, 0)):
+        x = np.arange(x0, x0 + n)
+        y = np.rint(150 + 6 * ((x - x0 - n / 2) / (n / 2)) ** 2 + rng.normal(0, 1.0, n)).astype(np.int32)
+        mask = (rng.random(n) > 0.1).astype(np.uint8)
+        if mask.sum() < 4:
+            mask[:] = 1
+        yd = torch.from_numpy(y).to(eng.device)
+        md = torch.from_numpy(mask).to(eng.device)
+        coef = eng.empty((4,), torch.float64)
+        resid = eng.empty((n,), torch.float64)
+        from solex_ser_recon_en_b200._lib import call
+        call('shg_polyfit3', yd.data_ptr(), md.data_ptr(), x0, n, coef.data_ptr(), yd.data_ptr(), resid.data_ptr(),
+             eng.stream)
+        ref = O.polyfit3(x[mask.astype(bool)], y[mask.astype(bool)])
+        got = coef.cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-9 if n < 10 else 0)
+        np.testing.assert_allclose(resid.cpu().numpy(), O.polyval_asc(x, got) - y, rtol=0, atol=1e-9)
+
+
+# ------------------------------------------------------------------ pass 2
+@pytest.mark.parametrize('impl', [1, 2])
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_recon_bit_exact(eng, name, impl):
+    g = golden(name)
+    _, stack = case_stack(name)
+    st = eng.ingest_array(stack, accumulate=False)
+    if impl == 2 and not st.geom.rotated:
+        pytest.skip('TMA band kernel handles rotated scans; the generic kernel covers H >= W')
+    shifts = [int(s) for s in g['shift']]
+    disk = eng.recon(st, g['fit'], shifts, impl=impl)
+    flip = CASES[name]['flip_x']
+    for i in range(len(shifts)):
+        img = u16(eng.to_reference_layout(disk[i], flip=flip))
+        assert np.array_equal(img, g[f'disk{i}']), f'shift {shifts[i]}'
+
+
+@pytest.mark.parametrize('impl', [1, 2])
+def test_recon_many_shifts_with_clipping(eng, impl):
+    """101 shifts on a narrow frame: the outer shifts clip at both borders
+    (clipped indices keep their weights, solex_util.py:116-123)."""
+    _, stack = case_stack('ser16_rot')
+    g = golden('ser16_rot')
+    shifts = O.shift_list(list(range(-50, 51)))
+    st = eng.ingest_array(stack, accumulate=False)
+    disk = eng.recon(st, g['fit'], shifts, impl=impl)
+    ref = O.recon(stack, g['fit'], shifts)
+    for i in range(len(shifts)):
+        assert np.array_equal(u16(disk[i]).T, ref[i]), f'shift {shifts[i]}'
+
+
+def test_recon_sparse_shift_list(eng):
+    """Shifts far apart exercise the multi-run TMA plan."""
+    _, stack = case_stack('ser16_rot')
+    g = golden('ser16_rot')
+    shifts = O.shift_list([-25, -24, 0, 3, 19, 20, 21])
+    st = eng.ingest_array(stack, accumulate=False)
+    ref = O.recon(stack, g['fit'], shifts)
+    for impl in (1, 2, 0):
+        disk = eng.recon(st, g['fit'], shifts, impl=impl)
+        for i in range(len(shifts)):
+            assert np.array_equal(u16(disk[i]).T, ref[i]), (impl, shifts[i])
+
+
+def test_recon_frame_ranges_tile_the_output(eng):
+    """Rank-style sharding: two stacks of frame ranges write disjoint frame rows of one disk."""
+    _, stack = case_stack('ser16_rot')
+    g = golden('ser16_rot')
+    shifts = [int(s) for s in g['shift']]
+    n = stack.shape[0]
+    disk = eng.alloc_disk(len(shifts), n, stack.shape[2])
+    disk.zero_()
+    for k0, k1 in ((0, 61), (61, n)):
+        st = eng.ingest_array(stack[k0:k1], n_total=n, k0=k0, accumulate=False)
+        eng.recon(st, g['fit'], shifts, disk=disk)
+    for i in range(len(shifts)):
+        assert np.array_equal(u16(disk[i]).T, g[f'disk{i}'])
+
+
+# ------------------------------------------------------------- layout ops
+def test_transpose_minmax_downscale(eng):
+    import torch
+    rng = np.random.default_rng(3)
+    for rows, cols in ((180, 416), (77, 130), (64, 64), (1, 9), (131, 2)):
+        a = rng.integers(5, 65000, size=(rows, cols)).astype(np.uint16)
+        d = torch.from_numpy(a).to(eng.device)
+        assert np.array_equal(u16(eng.to_reference_layout(d)), a.T)
+        assert np.array_equal(u16(eng.to_reference_layout(d, flip=True)), a.T[:, ::-1])
+        assert eng.minmax(d) == (int(a.min()), int(a.max()))
+        img = a.T                                                      # (ih, N) image of a frame-major disk
+        from oracle import thirdparty
+        want = thirdparty.downscale_local_mean(img.astype(np.float64), (4, 4)) * 16
+        assert np.array_equal(eng.downscale4(d, False).cpu().numpy(), np.rint(want).astype(np.int32))
+        want_f = thirdparty.downscale_local_mean(img[:, ::-1].astype(np.float64), (4, 4)) * 16
+        assert np.array_equal(eng.downscale4(d, True).cpu().numpy(), np.rint(want_f).astype(np.int32))
+
+
+# -------------------------------------------------------------------- warp
+def _warp_gpu(eng, disk_img, phi, ratio):
+    """disk_img: reference-layout (ih, N) uint16 ndarray."""
+    import torch
+    mat, mat3, (oh, ow), _, _ = O.warp_geometry(disk_img.shape, phi, ratio)
+    fm = torch.from_numpy(np.ascontiguousarray(disk_img.T)).to(eng.device)       # frame-major
+    lo, hi = eng.minmax(fm)
+    out = eng.warp(fm, False, mat3, (oh, ow), float(disk_img[0, 0]), lo, hi)
+    return u16(out)
+
+
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_warp_matches_reference(eng, name):
+    g = golden(name)
+    phi = 0.0 if math.isnan(float(g['slant'])) else math.radians(float(g['slant']))
+    ratio = float(g['ratio'])
+    shifts = [int(s) for s in g['shift']]
+    for sh in (int(s) for s in g['shift_requested']):
+        disk = g[f'disk{shifts.index(sh)}']
+        out = _warp_gpu(eng, disk, phi, ratio)
+        assert out.shape == g[f'circ_{sh}'].shape
+        assert np.array_equal(out, g[f'circ_{sh}'])
+
+
+@pytest.mark.parametrize('phi,ratio', [(0.0, 1.0), (0.12, 0.83), (-0.2, 1.31), (0.6, 1.05), (-0.7, 0.9), (0.0, 2.4)])
+def test_warp_against_oracle_random(eng, phi, ratio):
+    """Shear of either sign (m02 != 0 when a corner goes negative), squeeze and stretch,
+    flat regions equal to the global minimum (where skimage's clip matters)."""
+    rng = np.random.default_rng(int(abs(phi) * 100 + ratio * 10))
+    img = rng.integers(256, 60000, size=(150, 333)).astype(np.uint16)
+    img[40:60, 100:180] = img.min()
+    img[0, 0] = 4000
+    want, _ = O.warp_rows(img, phi, ratio)
+    got = _warp_gpu(eng, img, phi, ratio)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_warp_flip_reads_reversed_frames(eng):
+    import torch
+    rng = np.random.default_rng(9)
+    img = rng.integers(256, 60000, size=(96, 200)).astype(np.uint16)
+    flipped = img[:, ::-1]
+    want, mat3 = O.warp_rows(np.ascontiguousarray(flipped), 0.1, 1.2)
+    fm = torch.from_numpy(np.ascontiguousarray(img.T)).to(eng.device)
+    lo, hi = eng.minmax(fm)
+    out = eng.warp(fm, True, mat3, want.shape, float(flipped[0, 0]), lo, hi)
+    assert np.array_equal(u16(out), want)
+
+
+# ---------------------------------------------------------- transversalium
+def _transv_gpu(eng, circ, circle, borders, strength=301):
+    import torch
+    d = torch.from_numpy(circ).to(eng.device)
+    y1, y2, rows, xa, xb = eng.transversalium_chords(circle, borders)
+    stats = eng.transversalium_row_stats(d, rows, xa, xb)
+    ratios = np.concatenate([[0.0], stats])
+    gain = O.transversalium_gain(ratios, y1, y2, circ.shape[0], strength)
+    return ratios, gain, u16(eng.row_scale(d, gain))
+
+
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_transversalium_matches_reference(eng, name):
+    g = golden(name)
+    cercle = tuple(float(v) for v in g['cercle'])
+    for sh in (int(s) for s in g['shift_requested']):
+        circ = g[f'circ_{sh}']
+        if cercle == (-1.0, -1.0, -1.0):
+            circle, borders = (0, 0, 99999), [0, int(g['y1']) + 20, circ.shape[1] - 1, int(g['y2']) - 20]
+        else:
+            circle, borders = cercle, list(g['borders'])
+        ratios, gain, det = _transv_gpu(eng, circ, circle, borders)
+        _, _, ratios_ref = O.transversalium_rows(circ, circle, borders)
+        np.testing.assert_allclose(ratios, ratios_ref, rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(gain, g[f'gain_{sh}'], rtol=1e-5)              # north_star tolerance
+        diff = np.abs(det.astype(np.int32) - g[f'det_{sh}'].astype(np.int32))
+        assert diff.max() <= 1                                                    # north_star: <= 1 DN
+        assert (diff != 0).mean() < 1e-4
+
+
+def _row_stat_ref(a, b):
+    with np.errstate(divide='ignore', invalid='ignore'):
+        rat = np.log(a.astype(np.uint16) / b.astype(np.uint16))
+        return O.reject_outliers_mean(rat)
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 5, 31, 32, 33, 255, 256, 257, 1000, 1024, 1025, 5000, 26000, 40000])
+def test_row_stats_lengths_and_duplicates(eng, n):
+    """Chord lengths around every internal threshold (candidate list of 256,
+    block of 1024, shared-memory capacity -> global scratch), with heavy
+    duplication (few distinct pixel values, as in 8-bit scans)."""
+    import torch
+    import warnings
+    rng = np.random.default_rng(n)
+    img = np.empty((5, n + 3), np.uint16)
+    img[0] = rng.integers(20000, 20400, n + 3)
+    img[1] = rng.integers(20000, 20400, n + 3)
+    img[2] = rng.integers(78, 82, n + 3) * 256                 # 8-bit style: 4 distinct values
+    img[3] = rng.integers(78, 82, n + 3) * 256
+    img[4] = img[3]                                            # identical rows: rat == 0 everywhere, MAD == 0
+    img[1, 1::17] = 60000                                      # outliers
+    d = torch.from_numpy(img).to(eng.device)
+    rows = np.array([1, 2, 3, 4], np.int32)
+    xa = np.array([1, 0, 2, 1], np.int32)
+    xb = xa + n
+    got = eng.transversalium_row_stats(d, rows, xa, xb)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        want = np.array([_row_stat_ref(img[y, a:b], img[y - 1, a:b]) for y, a, b in zip(rows, xa, xb)])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13, equal_nan=True)
+
+
+def test_row_stats_zeros_inf_nan_empty(eng):
+    """Zeros in either row give +-inf / nan exactly as the reference's log(a/b)."""
+    import torch
+    import warnings
+    rng = np.random.default_rng(77)
+    n = 600
+    img = rng.integers(1000, 1100, size=(8, n)).astype(np.uint16)
+    img[1, 5] = 0                    # row 1 vs 0: -inf ; row 2 vs 1: +inf
+    img[3, 10] = 0; img[4, 10] = 0   # row 4 vs 3: nan
+    img[5, :400] = 0                 # row 5 vs 4: mostly -inf (median -inf) ; row 6 vs 5: mostly +inf
+    d = torch.from_numpy(img).to(eng.device)
+    rows = np.array([1, 2, 3, 4, 5, 6, 7, 7], np.int32)
+    xa = np.array([0, 0, 0, 0, 0, 0, 0, 50], np.int32)
+    xb = np.array([n, n, n, n, n, n, n, 50], np.int32)            # last chord is empty
+    got = eng.transversalium_row_stats(d, rows, xa, xb)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        want = np.array([_row_stat_ref(img[y, a:b], img[y - 1, a:b]) for y, a, b in zip(rows, xa, xb)])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13, equal_nan=True)
+
+
+def test_row_scale_clips_and_truncates(eng):
+    import torch
+    rng = np.random.default_rng(4)
+    for shape in ((33, 100), (64, 256), (7, 13)):
+        img = rng.integers(0, 65536, size=shape).astype(np.uint16)
+        gain = rng.uniform(0.7, 1.4, shape[0])
+        gain[0] = 1.0
+        got = u16(eng.row_scale(torch.from_numpy(img).to(eng.device), gain))
+        assert np.array_equal(got, O.apply_row_gain(img, gain))
+
+
+# ------------------------------------------------------------------ ingest
+@pytest.mark.parametrize('name', ['ser16_rot', 'ser8_rot_flip', 'ser16_norot'])
+def test_ingest_ser_file(eng, name, tmp_path):
+    from solex_ser_recon_en_b200.engine import ScanGeometry
+    _, stack = case_stack(name)
+    path = case_file(name, tmp_path)
+    info = O.ser_info(path)
+    geom = ScanGeometry(info['width'], info['height'], 1 if info['depth'] == 8 else 2, info['n_frames'])
+    st, stats = eng.ingest_file(path, geom, O.SER_HEADER_BYTES, slot_mb=1, n_slots=3, n_threads=3)
+    assert np.array_equal(st.host_frames(0, st.n), stack)
+    s_ref, m_ref = O.raw_sum_max(stack)
+    assert np.array_equal(st.sum.cpu().numpy().view(np.uint64).reshape(s_ref.shape), s_ref)
+    assert stats[2] == stack.nbytes
+    # a frame sub-range, as a rank would read it
+    st2, _ = eng.ingest_file(path, geom, O.SER_HEADER_BYTES, k0=50, n=60, slot_mb=1, n_slots=2, n_threads=2)
+    assert np.array_equal(st2.host_frames(0, 60), stack[50:110])
+
+
+def test_ingest_truncated_file_raises(eng, tmp_path):
+    from solex_ser_recon_en_b200.engine import ScanGeometry
+    from solex_ser_recon_en_b200._lib import ShgError
+    path = case_file('ser16_rot', tmp_path)
+    info = O.ser_info(path)
+    geom = ScanGeometry(info['width'], info['height'], 2, info['n_frames'] + 10)      # header lies
+    with pytest.raises(ShgError):
+        eng.ingest_file(path, geom, O.SER_HEADER_BYTES)
+
+
+# -------------------------------------------------- device-synthesised scans
+@pytest.mark.parametrize('bpp', [1, 2])
+def test_synth_scan_full_path_against_oracle(eng, bpp):
+    """A scan synthesised in HBM, read back, and pushed through the oracle:
+    mean / indices bit-exact, disks bit-exact."""
+    from solex_ser_recon_en_b200.engine import ScanGeometry
+    geom = ScanGeometry(640, 96, bpp, 400)
+    st = eng.synth_stack(geom, seed=7)
+    eng.accumulate(st)
+    mean_img, max_img = eng.finalize_mean_max(st.sum, st.max, st.n, geom)
+    stack = st.host_frames(0, st.n)
+    lf = O.mean_and_fit(stack)
+    assert np.array_equal(u16(mean_img), lf['mean_img'])
+    det = eng.detect_line(mean_img, max_img)
+    assert (det['y1'], det['y2']) == (lf['y1'], lf['y2'])
+    assert np.array_equal(det['min_intensity'].cpu().numpy(), lf['min_intensity'])
+    assert np.array_equal(det['min_sharp'].cpu().numpy(), lf['min_sharp'])
+    fit = eng.fit_line(det, geom.ih)
+    np.testing.assert_allclose(fit['p3'], lf['p3'], rtol=1e-6)
+    shifts = O.shift_list(list(range(-10, 11)))
+    disk = eng.recon(st, fit['fit'], shifts)
+    ref = O.recon(stack, fit['fit'], shifts)
+    for i in range(len(shifts)):
+        assert np.array_equal(u16(disk[i]).T, ref[i])
+
+
+def test_synth_is_range_consistent(eng):
+    """Frames synthesised as one range or as rank shards are identical."""
+    from solex_ser_recon_en_b200.engine import ScanGeometry
+    geom = ScanGeometry(256, 64, 2, 90)
+    whole = eng.synth_stack(geom, seed=3).host_frames(0, 90)
+    a = eng.synth_stack(geom, k0=0, n=40, seed=3).host_frames(0, 40)
+    b = eng.synth_stack(geom, k0=40, n=50, seed=3).host_frames(0, 50)
+    assert np.array_equal(np.concatenate([a, b]), whole)

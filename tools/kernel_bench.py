@@ -1,0 +1,109 @@
+"""Per-kernel timing on a device-synthesised scan (development aid; bench.py is
+the contract benchmark).  Prints achieved GB/s against the algorithmic bytes of
+SURVEY.md 8(d).
+
+    python tools/kernel_bench.py [--frames 20000] [--width 4096] [--height 512] [--shifts 50] [--reps 5]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from solex_ser_recon_en_b200.engine import ScanGeometry, get_engine   # noqa: E402
+
+
+def timed(fn, reps, flush=None):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(2):
+        fn()
+    for a, b in ev:
+        if flush is not None:
+            flush()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2], t[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--frames', type=int, default=20000)
+    ap.add_argument('--width', type=int, default=4096)
+    ap.add_argument('--height', type=int, default=512)
+    ap.add_argument('--bpp', type=int, default=2)
+    ap.add_argument('--shifts', type=int, default=50)
+    ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--impl', type=int, default=0)
+    ap.add_argument('--only', default='')
+    a = ap.parse_args()
+    eng = get_engine(0)
+    geom = ScanGeometry(a.width, a.height, a.bpp, a.frames)
+    st = eng.synth_stack(geom, seed=5)
+    eng.sync()
+    res = {}
+    only = set(a.only.split(',')) if a.only else None
+
+    def want(k):
+        return only is None or k in only
+
+    stack_bytes = a.frames * geom.frame_bytes
+    if want('accumulate'):
+        ms, best = timed(lambda: eng.accumulate(st), a.reps)
+        res['accumulate'] = dict(ms=ms, best_ms=best, GBps=stack_bytes / ms / 1e6)
+    eng.accumulate(st)
+    mean_img, max_img = eng.finalize_mean_max(st.sum, st.max, st.n, geom)
+    det = eng.detect_line(mean_img, max_img)
+    fit = eng.fit_line(det, geom.ih)
+    if want('detect'):
+        ms, best = timed(lambda: (eng.finalize_mean_max(st.sum, st.max, st.n, geom), eng.detect_line(mean_img, max_img),
+                                  eng.fit_line(det, geom.ih)), a.reps)
+        res['finalize+detect+fit'] = dict(ms=ms, best_ms=best)
+    shifts = list(dict.fromkeys([10, 0] + list(range(-a.shifts, a.shifts + 1))))
+    disk = eng.alloc_disk(len(shifts), a.frames, geom.ih)
+    nb = max(shifts) - min(shifts) + 2
+    recon_bytes = a.frames * (geom.ih * nb * a.bpp + len(shifts) * geom.ih * 2)
+    if want('recon'):
+        ms, best = timed(lambda: eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0, impl=a.impl), a.reps)
+        res['recon'] = dict(ms=ms, best_ms=best, GBps=recon_bytes / ms / 1e6, n_shifts=len(shifts), nb=nb)
+    eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0)
+    img_bytes = a.frames * geom.ih * 2
+    if want('minmax'):
+        ms, best = timed(lambda: eng.minmax(disk[1]), a.reps)
+        res['minmax'] = dict(ms=ms, best_ms=best, GBps=img_bytes / ms / 1e6)
+    # a plausible correction: Y/X ratio from the synthetic ellipse, small tilt
+    ratio = (0.40 * geom.ih) / (0.42 * a.frames)
+    phi = 0.02
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from solex_ser_recon_en_b200 import geometry as G
+    mat3, (oh, ow) = G.warp_plan((geom.ih, a.frames), phi, ratio)[1:3]
+    lo, hi = eng.minmax(disk[1])
+    circ = eng.empty((oh, ow), torch.uint16)
+    if want('warp'):
+        ms, best = timed(lambda: eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ), a.reps)
+        res['warp'] = dict(ms=ms, best_ms=best, GBps=(img_bytes + oh * ow * 2) / ms / 1e6, out=(oh, ow))
+    eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ)
+    cy, cx, rad = oh / 2.0, ow / 2.0, 0.40 * geom.ih
+    y1, y2, rows, xa, xb = eng.transversalium_chords((cx, cy, rad), [0, 0, ow - 1, oh - 1])
+    if want('transv'):
+        ms, best = timed(lambda: eng.transversalium_row_stats(circ, rows, xa, xb), a.reps)
+        res['transv_stats'] = dict(ms=ms, best_ms=best, GBps=2.0 * float((xb - xa).sum()) * 2 / ms / 1e6,
+                                   rows=len(rows), max_len=int((xb - xa).max()))
+    gain = np.ones(oh)
+    det_img = eng.empty((oh, ow), torch.uint16)
+    if want('scale'):
+        ms, best = timed(lambda: eng.row_scale(circ, gain, out=det_img), a.reps)
+        res['row_scale'] = dict(ms=ms, best_ms=best, GBps=2 * oh * ow * 2 / ms / 1e6)
+    if want('transpose'):
+        ms, best = timed(lambda: eng.to_reference_layout(disk[1]), a.reps)
+        res['transpose'] = dict(ms=ms, best_ms=best, GBps=2 * img_bytes / ms / 1e6)
+    print(json.dumps(dict(config=vars(a), results=res), indent=1))
+
+
+if __name__ == '__main__':
+    main()
