@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the frame-stack reconstruction hot path (BASELINE.json metric:
+frames/s of a full reconstruction, with HBM / PCIe roofline fractions).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on host cores
+
+Workload (config.workload): BASELINE.json configs[4] -- a synthetic 16-bit scan
+of 20 000 frames x 4096x512, H-alpha line, -w-50:50:1 (101 shift images), ellipse
+fit + circularisation + transversalium on.  It fits one B200 (84 GB stack +
+16.5 GB of disk images), so it is the N=1 workload; at N>1 the same 20 000
+frames are sharded by frame range across the ranks (strong scaling).
+
+One step = one pass of the whole path over the scan:
+  value : stack already resident in HBM (pass 1 re-reads it) -> mean/max -> all-reduce -> line detection + fit
+          -> reconstruction at 101 shifts -> gather to rank 0 -> ellipse fit -> warp + transversalium per shift.
+  e2e   : the same through the public entry points (Solex_recon.solex_read_reader / solex_process) starting from the
+          payload in pinned HOST memory (H2D inside the timed region, overlapped with pass 1) and ending with the
+          final images copied back to pinned host memory (D2H inside the timed region).
+Timed with CUDA events bracketed by barrier + synchronize, max over ranks.  The
+84 GB input is far larger than the 126 MB L2, so no explicit flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = dict(frames=20000, width=4096, height=512, bits=16, shift_lo=-50, shift_hi=50)
+METRIC = 'frames/sec, full reconstruction (mean + line fit + 101-shift recon + circularise + transversalium)'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    # development overrides (the driver never passes these; a run with them is labelled in config)
+    ap.add_argument('--frames', type=int, default=WORKLOAD['frames'])
+    ap.add_argument('--width', type=int, default=WORKLOAD['width'])
+    ap.add_argument('--height', type=int, default=WORKLOAD['height'])
+    ap.add_argument('--sample-frames', type=int, default=0, help='CPU arm: frames per step (0 = auto)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    shifts = list(range(WORKLOAD['shift_lo'], WORKLOAD['shift_hi'] + 1))
+    cfg = {
+        'workload': 'BASELINE configs[4]: synthetic 16-bit SER, %d frames x %dx%d, H-alpha, -w%d:%d:1 (%d shifts), '
+                    'ellipse fit + circularisation + transversalium' % (a.frames, a.width, a.height, shifts[0],
+                                                                        shifts[-1], len(shifts)),
+        'frames': a.frames, 'width': a.width, 'height': a.height, 'bits': 16, 'n_shifts': len(shifts),
+        'stack_bytes': a.frames * a.width * a.height * 2,
+        'l2_policy': 'inputs (84 GB stack) far larger than the 126 MB L2; no flush needed',
+    }
+    if (a.frames, a.width, a.height) != (WORKLOAD['frames'], WORKLOAD['width'], WORKLOAD['height']):
+        cfg['reduced'] = True
+    if extra:
+        cfg.update(extra)
+    return cfg, shifts
+
+
+def default_options(shifts):
+    """The reference's default options (SHG_MAIN.py:41-68) for a -c style run with no files written."""
+    from solex_ser_recon_en_b200 import SHG_MAIN
+    o = dict(SHG_MAIN.options)
+    o.update(shift=list(shifts), clahe_only=True, _nolog=True)
+    return o
+
+
+# =============================================================== clocks sampler
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, smax, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+# ================================================================== CPU arm
+def _cpu_worker(args):
+    """One host process: frames [k0, k1) of the sample.  phase 'sum' -> partial sum/max; phase 'recon' -> disks."""
+    from oracle import shg_oracle as O
+    phase, frames, fit, shifts = args
+    if phase == 'sum':
+        return O.raw_sum_max(frames)
+    return O.recon(frames, fit, shifts)
+
+
+def cpu_reference_step(sample, shifts, pool, n_workers):
+    """The reference's solex_read work (mean frame, line detection + fit, reconstruction at every shift) on a
+    frame sample, restated by the oracle and spread over the host cores by frame range."""
+    from oracle import shg_oracle as O
+    n = sample.shape[0]
+    cuts = [n * i // n_workers for i in range(n_workers + 1)]
+    parts = [sample[cuts[i]:cuts[i + 1]] for i in range(n_workers) if cuts[i + 1] > cuts[i]]
+    t0 = time.perf_counter()
+    res = list(pool.map(_cpu_worker, [('sum', p, None, None) for p in parts]))
+    s = sum(r[0] for r in res)
+    m = res[0][1]
+    for r in res[1:]:
+        m = np.maximum(m, r[1])
+    mean_img, max_img = O.finalize_mean_max(s, m, n, False)
+    y1, y2 = O.slit_extent(max_img)
+    mi, ms = O.line_minima(mean_img, y1, y2)
+    lf = O.line_fit(mi, ms, y1, y2, mean_img.shape[0])
+    all_shifts = O.shift_list(shifts)
+    list(pool.map(_cpu_worker, [('recon', p, lf['fit'], all_shifts) for p in parts]))
+    return time.perf_counter() - t0
+
+
+def make_cpu_sample(a, n_sample):
+    """Frames from the middle of the scan (so the Sun is in the slit), same recipe family as the device synth."""
+    from solex_ser_recon_en_b200 import synth
+    spec = synth.halpha(a.frames, a.width, a.height, seed=5)
+    spec.chunk = 8
+    k0 = (a.frames - n_sample) // 2
+    return synth.frames(spec, k0, k0 + n_sample)
+
+
+def run_reference_arm(a):
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    n_sample = a.sample_frames or 16 * workers
+    cfg, shifts = workload_config(a)
+    sample = make_cpu_sample(a, n_sample)
+    ctx = mp.get_context('fork')
+    times = []
+    with cf.ProcessPoolExecutor(max_workers=workers, mp_context=ctx) as pool:
+        for it in range(a.warmup + a.steps):
+            t = cpu_reference_step(sample, shifts, pool, workers)
+            if it >= a.warmup:
+                times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    value = n_sample / (ms / 1e3)
+    sample_desc = ('%d frames of %dx%d at %d shifts per step through the oracle port of solex_read (mean/max, line '
+                   'detection + cubic fit, reconstruction); circularisation + transversalium (O(1) in frame count) '
+                   'not included, which favours the CPU arm' % (n_sample, a.width, a.height, len(shifts)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': a.gpus,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': workers, 'kind': 'port', 'sample': sample_desc},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ================================================================== GPU arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from solex_ser_recon_en_b200 import Solex_recon, parallel
+    from solex_ser_recon_en_b200.engine import DeviceStack, ScanGeometry, get_engine
+    from solex_ser_recon_en_b200.solex_util import release_resident
+    from solex_ser_recon_en_b200.video_reader import device_scan, memory_scan
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    eng = get_engine(local)
+    cfg, shifts = workload_config(a)
+    geom = ScanGeometry(a.width, a.height, 2, a.frames)
+    k0, k1 = parallel.frame_range(a.frames, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- the scan, synthesised straight into HBM (this rank's frame range)
+    stack = eng.synth_stack(geom, k0=k0, n=k1 - k0, seed=5)
+    torch.cuda.synchronize()
+    results = {}
+
+    def sink(basefich, image, cercle):
+        results[basefich] = image                       # DeviceImage: final hot-path output of one shift
+        return None
+
+    def one_pass(reader, to_host):
+        opt = default_options(shifts)
+        opt['_result_sink'] = sink
+        results.clear()
+        disk_list, bounds, hdr = Solex_recon.solex_read_reader(reader, opt, 'bench')
+        if rank == 0:
+            Solex_recon.solex_process(opt, disk_list, bounds, hdr)
+            if to_host:
+                nbytes = 0
+                for im in results.values():
+                    nbytes += im.numpy().nbytes         # D2H into pinned memory
+                return nbytes
+        return 0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    def timed_loop(reader_factory, steps, warmup, to_host, label):
+        for _ in range(warmup):
+            one_pass(reader_factory(), to_host)
+        eng.profile_stages = True
+        eng.stage_report()
+        launches0 = eng.n_launches
+        barrier()
+        t_wall0 = time.time()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d2h = 0
+        for _ in range(steps):
+            d2h = one_pass(reader_factory(), to_host)
+        e1.record()
+        barrier()
+        t_wall1 = time.time()
+        ms = e0.elapsed_time(e1)
+        stages = eng.stage_report()
+        eng.profile_stages = False
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return dict(ms_per_step=ms / steps, stages={k: v / steps for k, v in stages.items()},
+                    launches=(eng.n_launches - launches0) // max(1, steps), d2h=d2h, wall=(t_wall0, t_wall1))
+
+    # ---- value: stack resident in HBM
+    dev = timed_loop(lambda: device_scan(stack), a.steps, a.warmup, False, 'device')
+
+    # ---- e2e: payload in pinned host memory -> H2D -> ... -> D2H
+    e2e = None
+    if not a.no_e2e:
+        nbytes = (k1 - k0) * geom.frame_bytes
+        host_ptr = eng.pinned_alloc(nbytes)               # exact size: 84 GB at N=1
+        eng.copy(host_ptr, stack.frames.data_ptr(), nbytes, 'd2h')
+        torch.cuda.synchronize()
+
+        def host_reader():
+            release_resident()
+            r = memory_scan(host_ptr - k0 * geom.frame_bytes, a.width, a.height, 16, a.frames)
+            r.device_stack = stack                      # refill the same HBM buffer (pinned-buffer / HBM reuse)
+            return r
+        e_steps = a.e2e_steps or a.steps
+        e2e = timed_loop(host_reader, e_steps, min(a.warmup, 3), True, 'e2e')
+        e2e['h2d'] = a.frames * geom.frame_bytes
+        if world > 1:
+            t = torch.tensor([float(e2e['d2h'])], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e['d2h'] = int(t.item())
+        eng.pinned_free(host_ptr)
+
+    # ---- roofline of the dominant kernel (pass-1 accumulation), timed live on its stream
+    acc_ms = []
+    for _ in range(3):
+        eng.accumulate(stack)
+    for _ in range(max(3, a.steps)):
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        eng.accumulate(stack)
+        s1.record()
+        torch.cuda.synchronize()
+        acc_ms.append(s0.elapsed_time(s1))
+    acc_bytes = (k1 - k0) * geom.frame_bytes
+    clocks = sampler.window(*dev['wall']) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'accumulate_traffic.json'))).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        in_step = dev['stages'].get('accumulate')
+        t_acc = float(np.mean(acc_ms))
+        achieved = acc_bytes / (t_acc * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': a.frames / (dev['ms_per_step'] * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dev['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic', 'config': cfg,
+            'clocks': clocks, 'gpu_launches': dev['launches'],
+            'stages_ms': {k: round(v, 3) for k, v in sorted(dev['stages'].items())},
+            'roofline': {'bound': 'hbm', 'kernel': 'accumulate_u16_kernel (pass 1: integer sum + max of the stack)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': acc_bytes, 'ms_per_launch': t_acc,
+                         'ms_per_launch_inside_step': in_step, 'frac_of_8TBps_nominal': achieved / 8000.0},
+        }
+        if e2e is not None:
+            line['e2e'] = {'value': a.frames / (e2e['ms_per_step'] * 1e-3), 'unit': 'frames/s',
+                           'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
+                           'ms_per_step': e2e['ms_per_step'],
+                           'h2d_GBps': e2e['h2d'] / (e2e['ms_per_step'] * 1e-3) / 1e9,
+                           'stages_ms': {k: round(v, 3) for k, v in sorted(e2e['stages'].items())}}
+        if world == 1 and not a.no_cpu:
+            line['cpu_baseline'] = cpu_baseline_subprocess(a)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline_subprocess(a):
+    """The CPU arm on a bounded sample in a clean child process (no CUDA context to fork)."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '1',
+           '--frames', str(a.frames), '--width', str(a.width), '--height', str(a.height)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK='0'))
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        return {'error': (out.stderr or 'no output')[-300:]}
+    except Exception as e:
+        return {'error': repr(e)}
+
+
+def main():
+    a = parse_args()
+    if a.impl == 'reference':
+        return run_reference_arm(a)
+    return run_b200(a)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -162,6 +162,13 @@ int shg_ingest_memory(shg_ingest* ing, const void* h_payload, int64_t frame_byte
                       int64_t frame_stride_bytes, int64_t n_frames, void* d_stack, int bytes_per_px,
                       uint64_t* d_sum, uint32_t* d_max, double* h_stats4);
 
+/* Pinned host memory of an exact size (cudaHostAlloc, portable) for payloads
+ * and result images, and a stream-ordered copy in either direction
+ * (kind: 1 = host->device, 2 = device->host, 3 = device->device). */
+int shg_host_alloc(int64_t bytes, void** out);
+int shg_host_free(void* p);
+int shg_memcpy_async(void* dst, const void* src, int64_t bytes, int kind, void* stream);
+
 /* ---- synthetic scans on the device (bench / full-size property tests) --- */
 /* Fills frames [k0, k0+n) of a synthetic scan of n_total frames (same recipe
  * family as solex_ser_recon_en_b200/synth.py, hash noise). */

@@ -1,0 +1,192 @@
+"""Drop-in for the reference's Solex_recon module (/root/reference/Solex_recon.py):
+solex_do_work, solex_read, solex_process, single_image_process with the same
+arguments, return values, `options` mutations and log lines.
+
+Differences that follow from running on a GPU:
+ * the reference post-processes in a forked multiprocessing.Pool(4)
+   (Solex_recon.py:30-42); a forked child cannot use the parent's CUDA context,
+   so the GPU stages of solex_process run in the calling process and only the
+   host tail (CLAHE, PNG / FITS writers) is handed to worker threads, which
+   keeps the reference's overlap of "read file i+1 while file i is written";
+ * disk images are DeviceImage array-likes: they stay in HBM until a writer or
+   a caller asks for the pixels.
+"""
+from __future__ import annotations
+
+import math
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import fits_min as fits
+from . import parallel, postprocess
+from .device_image import DeviceImage
+from .ellipse_to_circle import correct_image, ellipse_to_circle
+from .solex_util import (clearlog, compute_mean_return_fit, correct_transversalium2, image_process, logme,
+                         make_header, output_path, read_video_improved, write_complete)
+from .video_reader import video_reader
+
+
+def solex_do_work(tasks, flag_command_line=False):
+    """Process a list of (file, options) tasks; returns None, raises on the first bad file
+    like the reference (the caller's try/except reports it)."""
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        pending = []
+        for file, options in tasks:
+            print('file %s is processing' % file)
+            disk_list, backup_bounds, hdr = solex_read(file, options)
+            if parallel.world()[0] != 0:
+                continue                                     # rows were gathered to rank 0
+            pending += solex_process(options, disk_list, backup_bounds, hdr, _pool=pool)
+        for fut in pending:
+            fut.result()
+
+
+def solex_read(file, options):
+    """Mean frame + line fit + reconstruction of one scan.
+    Returns (disk_list, (y1, y2), hdr); mutates options['basefich0'],
+    ['shift_requested'] and ['shift'] exactly as the reference (Solex_recon.py:49-83)."""
+    return solex_read_reader(video_reader(file), options, os.path.splitext(file)[0])
+
+
+def solex_read_reader(rdr, options, basefich0):
+    """solex_read on an already opened reader (a video_reader, or a
+    video_reader.memory_scan wrapping a payload that sits in host memory)."""
+    options['basefich0'] = basefich0
+    log = basefich0 + '_log.txt'
+    clearlog(log, options)
+    logme(log, options, 'Pixel shift : ' + str(options['shift']))
+    options['shift_requested'] = options['shift']
+    options['shift'] = list(dict.fromkeys([options['ellipse_fit_shift'], 0] + options['shift']))
+    hdr = make_header(rdr)
+    mean_img, fit, backup_y1, backup_y2 = compute_mean_return_fit(rdr, options, hdr, rdr.iw, rdr.ih, basefich0)
+    disk_list, ih, iw, _ = read_video_improved(rdr, fit, options)
+    hdr['NAXIS1'] = iw
+    for i in range(len(disk_list)):
+        if options['flip_x']:
+            disk_list[i] = disk_list[i].flipped() if isinstance(disk_list[i], DeviceImage) \
+                else np.flip(disk_list[i], axis=1)
+        if options['save_fit'] and options['shift'][i] in options['shift_requested']:
+            basefich = basefich0 + '_shift=' + str(options['shift'][i])
+            fits.PrimaryHDU(np.asarray(disk_list[i]), header=hdr).writeto(
+                output_path(basefich + '_raw.fits', options), overwrite='True')
+    return disk_list, (backup_y1, backup_y2), hdr
+
+
+def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
+    """Circularise, de-transversalium, crop and write every requested shift
+    (Solex_recon.py:93-133).  With `_pool` the host tail of each image is
+    submitted to it and the futures are returned; otherwise it runs inline and
+    the return value is None like the reference's."""
+    basefich0 = options['basefich0']
+    log = basefich0 + '_log.txt'
+    if options['transversalium']:
+        logme(log, options, 'Transversalium correction : ' + str(options['trans_strength']))
+    else:
+        logme(log, options, 'Transversalium disabled')
+    logme(log, options, 'Mirror X : ' + str(options['flip_x']))
+    logme(log, options, 'Post-rotation : ' + str(options['img_rotate']) + ' degrees')
+    logme(log, options, f'Protus adjustment : {options["delta_radius"]}')
+    logme(log, options, f'de-vignette : {options["de-vignette"]}')
+    if options['de-vignette']:
+        raise Exception('de-vignette is a GUI-only option of the reference and is not part of this path')
+    borders = [0, 0, 0, 0]
+    cercle0 = (-1, -1, -1)
+    shifts = options['shift']
+    requested = [i for i in range(len(disk_list)) if shifts[i] in options['shift_requested']]
+    circular = {}
+    # 1. geometry: disk_list[0] is the ellipse-fit shift; the fit is made once and reused
+    if options['ratio_fixe'] is None and options['slant_fix'] is None:
+        basefich = basefich0 + '_shift=' + str(shifts[0])
+        circular[0], cercle0, options['ratio_fixe'], phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+        options['slant_fix'] = math.degrees(phi)
+        todo = [i for i in requested if i != 0]
+    else:
+        todo = list(requested)
+    ratio = options['ratio_fixe'] if options['ratio_fixe'] is not None else 1.0
+    phi = math.radians(options['slant_fix']) if options['slant_fix'] is not None else 0.0
+    # 2. circularise every other requested shift with that geometry (batched)
+    if todo:
+        if todo[0] == 0:                                      # the reference logs the matrix for i == 0 only
+            circular[0] = correct_image(disk_list[0], phi, ratio, np.array([-1.0, -1.0]), -1.0, options,
+                                        print_log=True)[0]
+            todo = todo[1:]
+        warped, _, _, _ = postprocess.circularise_many([disk_list[i] for i in todo], phi, ratio)
+        circular.update(zip(todo, warped))
+    # 3. transversalium for all requested shifts (batched), then the host tail per image
+    images = [circular[i] for i in requested]
+    if options['transversalium'] and images and all(isinstance(im, DeviceImage) for im in images) \
+            and not options['save_fit']:
+        if not cercle0 == (-1, -1, -1):
+            circle, bord = cercle0, borders
+        else:
+            circle = (0, 0, 99999)
+            bord = [0, backup_bounds[0] + 20, images[0].shape[1] - 1, backup_bounds[1] - 20]
+        detrans, gains = postprocess.detransversalium_many(images, circle, bord, options['trans_strength'])
+        options['_transversalium_cache'] = gains[-1]
+        options['_transversalium_gains'] = {shifts[i]: gains[j] for j, i in enumerate(requested)}
+    else:
+        detrans = None
+    futures = []
+    for j, i in enumerate(requested):
+        basefich = basefich0 + '_shift=' + str(shifts[i])
+        res = single_image_process(images[j], hdr, options, cercle0, borders, basefich, backup_bounds, _pool=_pool,
+                                   _detrans=None if detrans is None else detrans[j])
+        if _pool is not None:
+            futures.append(res)
+        write_complete(log, options)
+    return futures if _pool is not None else None
+
+
+def _crop(img, cercle, options):
+    """Square / fixed-width crop centred on the disk (Solex_recon.py:155-171)."""
+    h, w = img.shape
+    nw = h if options['fixed_width'] is None else options['fixed_width']
+    half = nw // 2
+    cx = w // 2 if cercle == (-1, -1, -1) else int(cercle[0])
+    shift = half - cx
+    out = np.full((h, nw), img[0, 0], dtype=img.dtype)
+    a, b = max(0, cx - half), min(cx + half, w)
+    out[:, :b - a] = img[:, a:b]
+    if shift > 0:
+        out = np.roll(out, shift, axis=1)
+        out[:, :shift] = img[0, 0]
+    if not cercle == (-1, -1, -1):
+        cercle = (half, cercle[1], cercle[2])
+    return out, cercle
+
+
+def single_image_process(frame_circularized, hdr, options, cercle0, borders, basefich, backup_bounds, _pool=None,
+                         _detrans=None):
+    """Transversalium correction on the GPU, then the host tail
+    (Solex_recon.py:136-174).  Returns image_process's (cc, frame_protus), or a
+    future of it when a pool is given.  `_detrans` carries the already corrected
+    image when solex_process batched that stage."""
+    if options['save_fit']:
+        fits.PrimaryHDU(np.asarray(frame_circularized), header=hdr).writeto(
+            output_path(basefich + '_circular.fits', options), overwrite='True')
+    if _detrans is not None:
+        detrans = _detrans
+    elif options['transversalium']:
+        if not cercle0 == (-1, -1, -1):
+            detrans = correct_transversalium2(frame_circularized, cercle0, borders, options, 0, basefich)
+        else:
+            detrans = correct_transversalium2(
+                frame_circularized, (0, 0, 99999),
+                [0, backup_bounds[0] + 20, frame_circularized.shape[1] - 1, backup_bounds[1] - 20], options, 0, basefich)
+    else:
+        detrans = frame_circularized
+    sink = options.get('_result_sink')
+    if sink is not None:                                      # callers that want the hot-path result itself
+        return sink(basefich, detrans, cercle0)
+    host = np.asarray(detrans)                                # the one device -> host copy of this image
+    if options['save_fit'] and options['transversalium']:
+        fits.PrimaryHDU(host, header=hdr).writeto(output_path(basefich + '_detransversaliumed.fits', options),
+                                                  overwrite='True')
+    cercle = cercle0
+    if options['fixed_width'] is not None or options['crop_width_square']:
+        host, cercle = _crop(host, cercle, options)
+    if _pool is not None:
+        return _pool.submit(image_process, host, cercle, dict(options), hdr, basefich)
+    return image_process(host, cercle, options, hdr, basefich)

@@ -51,6 +51,9 @@ _PROTOS = {
     'shg_ingest_destroy': (i32, [vp]),
     'shg_ingest_file': (i32, [vp, C.c_char_p, i64, i64, i64, i64, i64, vp, i32, vp, vp, C.POINTER(dbl)]),
     'shg_ingest_memory': (i32, [vp, vp, i64, i64, i64, vp, i32, vp, vp, C.POINTER(dbl)]),
+    'shg_host_alloc': (i32, [i64, C.POINTER(vp)]),
+    'shg_host_free': (i32, [vp]),
+    'shg_memcpy_async': (i32, [vp, vp, i64, i32, vp]),
     'shg_synth_fill': (i32, [vp, i32, i64, i64, i64, i32, i32, u64, vp]),
 }
 

@@ -220,3 +220,22 @@ extern "C" int shg_ingest_memory(shg_ingest* ing, const void* h_payload, int64_t
     return run_ingest(ing, -1, static_cast<const unsigned char*>(h_payload), 0, frame_bytes, frame_stride_bytes, 0,
                       n_frames, d_stack, bytes_per_px, d_sum, d_max, h_stats4);
 }
+
+extern "C" int shg_host_alloc(int64_t bytes, void** out) {
+    SHG_REQUIRE(out && bytes > 0, "shg_host_alloc: bad arguments");
+    SHG_CHECK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+extern "C" int shg_host_free(void* p) {
+    if (p) SHG_CHECK(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int shg_memcpy_async(void* dst, const void* src, int64_t bytes, int kind, void* stream) {
+    SHG_REQUIRE(kind >= 1 && kind <= 3, "shg_memcpy_async: kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost
+                                                                            : cudaMemcpyDeviceToDevice;
+    SHG_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, k, as_stream(stream)));
+    return 0;
+}

@@ -1,0 +1,121 @@
+"""Drop-in for the reference's ellipse_to_circle module
+(/root/reference/ellipse_to_circle.py): ellipse_to_circle, correct_image,
+get_correction_matrix, two_step keep their signatures and return values; the
+warp runs on the GPU (shg_warp_rows) and the limb fit works from 4x4 block
+sums computed on the GPU.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import ellipse_fit, geometry
+from .device_image import DeviceImage
+from .engine import get_engine
+from .solex_util import logme, output_path
+
+NUM_REG = ellipse_fit.NUM_REG
+rot = geometry.rotation
+get_correction_matrix = geometry.correction_matrix
+two_step = ellipse_fit.two_step
+
+
+def _as_frames(eng, image):
+    """(frame-major tensor, flip) for a DeviceImage or an (ih, N) array.  Arrays
+    in [0, 1) (the reference passes disk / 65536) are scaled back to DN."""
+    import torch
+    if isinstance(image, DeviceImage):
+        if image.layout == 'frames':
+            return image.tensor, image.flip
+        host = image.numpy()
+    else:
+        host = np.asarray(image)
+    if host.dtype.kind == 'f':
+        host = np.rint(host * 65536.0) if host.size and host.max() < 1.0 + 1e-9 else host
+    dn = np.ascontiguousarray(host.T).astype(np.uint16)
+    return torch.from_numpy(dn).to(eng.device), False
+
+
+def correct_image(image, phi, ratio, center, height, options, print_log=False):
+    """Shear / scale the image along the scan axis so that the Sun is round
+    (reference ellipse_to_circle.py:94-145).  Returns
+    (uint16 image, (cx, cy, radius), mat3); the image is a DeviceImage when the
+    input was one, else an ndarray."""
+    eng = get_engine()
+    frames, flip = _as_frames(eng, image)
+    n, ih = frames.shape
+    mat, mat3, out_shape, _, theta = geometry.warp_plan((ih, n), phi, ratio)
+    lo, hi = eng.minmax(frames)
+    corner = frames[n - 1 if flip else 0, 0:1].cpu().numpy()[0]              # image[0, 0]
+    out = eng.warp(frames, flip, mat3, out_shape, float(corner), lo, hi)
+    new_center, new_radius = geometry.moved_circle(np.asarray(center, dtype='d'), height, phi, ratio, (ih, n))
+    if print_log:
+        basefich0 = options['basefich0']
+        log = basefich0 + '_log.txt'
+        print('unrotation angle theta = ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
+        np.set_printoptions(suppress=True)
+        logme(log, options, 'Y/X ratio : ' + '{:.3f}'.format(ratio))
+        print('Y/X ratio : ' + '{:.3f}'.format(ratio))
+        logme(log, options, 'Tilt angle : ' + '{:.3f}'.format(math.degrees(phi)) + ' degrees')
+        logme(log, options, 'Linear transform correction matrix : \n' + str(mat))
+        where = (str(new_center) + ', ' + '{:.3f}'.format(new_radius)) if not height == -1.0 else 'UNKNOWN'
+        logme(log, options, 'Disk position, radius : ' + where)
+        logme(log, options, 'Unrotation : ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
+        np.set_printoptions(suppress=False)
+    result = DeviceImage(eng, out) if isinstance(image, DeviceImage) else out.cpu().numpy()
+    return result, (new_center[0], new_center[1], new_radius), mat3
+
+
+def ellipse_to_circle(image, options, basefich):
+    """Fit an ellipse to the solar limb and circularise
+    (reference ellipse_to_circle.py:294-342).
+    Returns (image, (cx, cy, radius), ratio, phi, borders)."""
+    eng = get_engine()
+    frames, flip = _as_frames(eng, image)
+    with eng.stage('ellipse_fit(host)'):
+        sums = eng.downscale4(frames, flip).cpu().numpy()
+        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_block_sums(sums)
+    src = image if isinstance(image, DeviceImage) else DeviceImage(eng, frames, 'frames', flip)
+    fixed, circle, mat3 = correct_image(src, phi, ratio, center, height, options, print_log=True)
+    pts = np.ones((kept.shape[0], 3))
+    pts[:, 0], pts[:, 1] = kept[:, 1], kept[:, 0]                             # (row, col) -> (x, y)
+    moved = (np.linalg.inv(mat3) @ pts.T).T
+    borders = [np.min(moved[:, 0]), np.min(moved[:, 1]), np.max(moved[:, 0]), np.max(moved[:, 1])]
+    print('sun borders found:' + str(borders))
+    if not options['clahe_only'] and not options['protus_only']:
+        _plot_fit(image, fixed, raw, kept, outline, borders, output_path(basefich + '_ellipse_fit.png', options))
+    if not isinstance(image, DeviceImage):
+        fixed = np.asarray(fixed)
+    return fixed, circle, ratio, phi, borders
+
+
+def _plot_fit(image, fixed, raw, kept, outline, borders, path):
+    try:
+        import matplotlib.figure
+        import matplotlib.pyplot
+    except Exception:
+        return                                                                # diagnostic plot only
+    image, fixed = np.asarray(image), np.asarray(fixed)
+    fig = matplotlib.figure.Figure()
+    ax = [[fig.add_subplot(2, 2, 1), fig.add_subplot(2, 2, 2)], [fig.add_subplot(2, 2, 3), fig.add_subplot(2, 2, 4)]]
+    fig.tight_layout()
+    gray = matplotlib.pyplot.cm.gray
+    ax[0][0].imshow(image, cmap=gray)
+    ax[0][0].set_title('uncorrected image', fontsize=11)
+    ax[0][1].imshow(image, cmap=gray)
+    ax[0][1].plot(raw[:, 1], raw[:, 0], 'ro', label='edge detection')
+    ax[0][1].legend(prop={'size': 6})
+    ax[1][1].plot(kept[:, 1], kept[:, 0], 'ro', label='filtered edges')
+    ax[1][1].plot(outline[:, 1], outline[:, 0], color='b', label='ellipse fit')
+    ax[1][1].set_ylim([image.shape[0], 0])
+    ax[1][1].legend(prop={'size': 6})
+    ax[1][0].imshow(fixed, cmap=gray)
+    for y in (borders[1], borders[3]):
+        ax[1][0].axhline(y=y)
+    for x in (borders[0], borders[2]):
+        ax[1][0].axvline(x=x)
+    ax[1][0].set_title('geometrically corrected image', fontsize=11)
+    for a in (ax[0][0], ax[0][1], ax[1][0], ax[1][1]):
+        a.set_aspect('equal')
+    fig.savefig(path, dpi=300)

@@ -82,6 +82,26 @@ def _ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+class _Stage:
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if getattr(self.eng, 'profile_stages', False):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.eng.device))
+        return self
+
+    def __exit__(self, *exc):
+        if getattr(self.eng, 'profile_stages', False):
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(torch.cuda.current_stream(self.eng.device))
+            if not hasattr(self.eng, '_stage_events'):
+                self.eng._stage_events = []
+            self.eng._stage_events.append((self.name, self.a, b))
+        return False
+
+
 class Engine:
     """One per process / GPU."""
 
@@ -103,6 +123,20 @@ class Engine:
         self.n_launches = 0            # kernels launched through this engine (bench's gpu_launches)
 
     # ------------------------------------------------------------------ util
+    def stage(self, name):
+        """Context manager: when self.stage_times is a dict, brackets the block
+        with CUDA events on the current stream and accumulates its milliseconds
+        (read after a synchronize through stage_report())."""
+        return _Stage(self, name)
+
+    def stage_report(self):
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, a, b in getattr(self, '_stage_events', []):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        self._stage_events = []
+        return out
+
     @property
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -114,6 +148,20 @@ class Engine:
         torch.cuda.synchronize(self.device)
 
     # ---------------------------------------------------------------- ingest
+    def pinned_alloc(self, nbytes: int) -> int:
+        """Exact-size pinned host buffer (freed with pinned_free)."""
+        p = C.c_void_p()
+        call('shg_host_alloc', int(nbytes), C.byref(p))
+        return int(p.value)
+
+    @staticmethod
+    def pinned_free(ptr: int):
+        call('shg_host_free', int(ptr))
+
+    def copy(self, dst_ptr: int, src_ptr: int, nbytes: int, kind: str):
+        call('shg_memcpy_async', int(dst_ptr), int(src_ptr), int(nbytes), {'h2d': 1, 'd2h': 2, 'd2d': 3}[kind],
+             self.stream)
+
     def _ring(self, slot_bytes, n_slots, n_threads):
         cfg = (int(slot_bytes), int(n_slots), int(n_threads))
         if self._ingest is not None and self._ingest_cfg == cfg:
@@ -318,6 +366,15 @@ class Engine:
         lo, hi = mm.cpu().tolist()
         return int(lo), int(hi)
 
+    def minmax_many(self, disk):
+        """(lo, hi) of every image of a (S, N, ih) disk tensor with one device -> host copy."""
+        n = disk.shape[0]
+        mm = torch.tensor([[65535, 0]] * n, dtype=torch.int32, device=self.device)
+        for i in range(n):
+            call('shg_minmax_u16', disk[i].data_ptr(), disk[i].numel(), mm[i].data_ptr(), self.stream)
+        self.n_launches += n
+        return mm.cpu().numpy()
+
     # -------------------------------------------------- circularisation warp
     def warp(self, disk_s, flip: bool, mat3: np.ndarray, out_shape, cval: float, lo: float, hi: float, out=None):
         """correct_image's pixel work (ellipse_to_circle.py:112-118) on a
@@ -383,10 +440,33 @@ class Engine:
         self.n_launches += 1
         return out.cpu().numpy()
 
+    def transversalium_row_stats_many(self, imgs, rows, xa, xb):
+        """Same chords on several images (every shift of one scan shares the
+        circle): one launch per image, one device -> host copy.  Returns (S, n)."""
+        n = len(rows)
+        if n == 0 or len(imgs) == 0:
+            return np.zeros((len(imgs), 0))
+        h, w = imgs[0].shape
+        if rows.min() < 1 or rows.max() >= h or xa.min() < 0 or xb.max() > w:
+            raise IndexError('transversalium chord outside the image')
+        idx = torch.from_numpy(np.stack([rows, xa, xb])).to(self.device)
+        out = self.empty((len(imgs), n), torch.float64)
+        max_len = int(max(0, (xb - xa).max()))
+        wb = int(lib.shg_transv_workspace_bytes(n, max_len))
+        work = self.empty((wb,), torch.uint8) if wb > 0 else None
+        tab = self.logtab.data_ptr()
+        for i, img in enumerate(imgs):
+            assert tuple(img.shape) == (h, w)
+            call('shg_transv_row_stats', img.data_ptr(), h, w, idx[0].data_ptr(), idx[1].data_ptr(),
+                 idx[2].data_ptr(), n, max_len, tab, out[i].data_ptr(), _ptr(work), wb, self.stream)
+        self.n_launches += len(imgs)
+        return out.cpu().numpy()
+
     def row_scale(self, img, gain: np.ndarray, out=None):
         """(img.T * c).T, clip 65535, truncate (solex_util.py:489,515-516)."""
         h, w = img.shape
-        g = torch.from_numpy(np.ascontiguousarray(gain, dtype=np.float64)).to(self.device)
+        g = gain if isinstance(gain, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(gain, dtype=np.float64)).to(self.device)
         if out is None:
             out = self.empty((h, w), torch.uint16)
         call('shg_row_scale_u16', img.data_ptr(), h, w, g.data_ptr(), out.data_ptr(), self.stream)

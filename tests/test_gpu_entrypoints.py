@@ -1,0 +1,154 @@
+"""GPU: the drop-in entry points (video_reader -> Solex_recon.solex_read ->
+solex_process) against the arrays recorded at the same seams of the unmodified
+reference (tests/golden, made by oracle/make_golden.py), including the
+`options` side effects and the log file."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+from oracle.make_golden import CASES
+from helpers import ALL_CASES, case_file, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def options_for(name, tmp_path, **over):
+    case = CASES[name]
+    o = ref_shim.default_options(shift=list(case['shift']), flip_x=case['flip_x'], ratio_fixe=case.get('ratio_fixe'))
+    o.pop('_nolog')
+    o['output_dir'] = str(tmp_path)
+    o.update(over)
+    return o
+
+
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_solex_read_matches_reference(name, tmp_path):
+    from solex_ser_recon_en_b200 import Solex_recon
+    g = golden(name)
+    path = case_file(name, tmp_path)
+    opt = options_for(name, tmp_path)
+    disk_list, bounds, hdr = Solex_recon.solex_read(path, opt)
+    assert [int(s) for s in opt['shift']] == [int(s) for s in g['shift']]
+    assert opt['shift_requested'] == list(CASES[name]['shift'])
+    assert opt['basefich0'] == os.path.splitext(path)[0]
+    assert (int(bounds[0]), int(bounds[1])) == (int(g['y1']), int(g['y2']))
+    assert hdr['NAXIS1'] == int(g['iw']) and hdr['NAXIS2'] == int(g['ih'])
+    assert len(disk_list) == len(opt['shift'])
+    for i, d in enumerate(disk_list):
+        a = np.asarray(d)
+        assert a.dtype == np.uint16 and a.shape == (int(g['ih']), int(g['n']))
+        assert np.array_equal(a, g[f'disk{i}']), f'shift {opt["shift"][i]}'
+    log = open(os.path.join(str(tmp_path), os.path.basename(opt['basefich0']) + '_log.txt')).read()
+    assert 'Pixel shift : ' + str(list(CASES[name]['shift'])) in log
+    assert 'Number of frames : %d' % int(g['n']) in log
+    assert 'Vertical limits y1, y2 : %d %d' % (int(g['y1']), int(g['y2'])) in log
+    assert 'Spectral line polynomial fit: [' in log
+
+
+@pytest.mark.parametrize('name', ALL_CASES)
+def test_solex_process_matches_reference(name, tmp_path):
+    """Circularised and detransversaliumed images per requested shift, the
+    ellipse geometry written back into `options`, and the gain vector."""
+    from solex_ser_recon_en_b200 import Solex_recon
+    g = golden(name)
+    path = case_file(name, tmp_path)
+    opt = options_for(name, tmp_path, save_fit=True)
+    disk_list, bounds, hdr = Solex_recon.solex_read(path, opt)
+    seen = {}
+    real = Solex_recon.single_image_process
+
+    def spy(frame_circularized, hdr_, options, cercle0, borders, basefich, backup_bounds, _pool=None):
+        sh = int(basefich.rsplit('_shift=', 1)[1])
+        out = real(frame_circularized, hdr_, options, cercle0, borders, basefich, backup_bounds, _pool=_pool)
+        seen[sh] = (np.asarray(frame_circularized), np.array(options['_transversalium_cache']),
+                    np.array(cercle0, dtype='d'), np.array(borders, dtype='d'))
+        return out
+
+    Solex_recon.single_image_process = spy
+    try:
+        assert Solex_recon.solex_process(opt, disk_list, bounds, hdr) is None
+    finally:
+        Solex_recon.single_image_process = real
+    assert sorted(seen) == sorted(int(s) for s in g['shift_requested'])
+    np.testing.assert_allclose(float(opt['ratio_fixe']), float(g['ratio']), rtol=1e-9)
+    if not math.isnan(float(g['slant'])):
+        np.testing.assert_allclose(float(opt['slant_fix']), float(g['slant']), rtol=1e-6, atol=1e-9)
+    for sh, (circ, gain, cercle, borders) in seen.items():
+        want = g[f'circ_{sh}']
+        assert circ.shape == want.shape and circ.dtype == np.uint16
+        assert np.abs(circ.astype(np.int32) - want.astype(np.int32)).max() <= 1          # north_star: <= 1 DN
+        assert np.mean(circ != want) < 1e-3
+        np.testing.assert_allclose(gain, g[f'gain_{sh}'], rtol=1e-5)                      # north_star: 1e-5 relative
+        np.testing.assert_allclose(cercle, g['cercle'], rtol=1e-9)
+        np.testing.assert_allclose(borders, g['borders'], rtol=1e-9, atol=1e-9)
+        # -f output: the detransversaliumed FITS holds the final hot-path image
+        from solex_ser_recon_en_b200 import fits_min
+        det_path = os.path.join(str(tmp_path), os.path.basename(opt['basefich0']) + f'_shift={sh}_detransversaliumed.fits')
+        det = read_fits_u16(det_path)
+        d = np.abs(det.astype(np.int32) - g[f'det_{sh}'].astype(np.int32))
+        assert d.max() <= 1 and np.mean(d != 0) < 1e-3
+        assert os.path.exists(os.path.join(str(tmp_path), os.path.basename(opt['basefich0']) + f'_shift={sh}_clahe.png'))
+    log = open(os.path.join(str(tmp_path), os.path.basename(opt['basefich0']) + '_log.txt')).read()
+    assert 'Transversalium correction : 301' in log and 'Mirror X : ' + str(CASES[name]['flip_x']) in log
+    assert 'Y/X ratio : ' + '{:.3f}'.format(float(g['ratio'])) in log
+    assert 'end time: ' in log
+
+
+def read_fits_u16(path):
+    raw = open(path, 'rb').read()
+    head_end = raw.index(b'END' + b' ' * 77) + 80
+    head_len = (head_end + 2879) // 2880 * 2880
+    cards = {raw[i:i + 8].strip().decode(): raw[i + 10:i + 30].strip().decode() for i in range(0, head_end, 80)}
+    w, h = int(cards['NAXIS1']), int(cards['NAXIS2'])
+    data = np.frombuffer(raw, dtype='>i2', count=w * h, offset=head_len).reshape(h, w)
+    return (data.astype(np.int32) + int(float(cards.get('BZERO', '0')))).astype(np.uint16)
+
+
+def test_solex_do_work_batch_and_flags(tmp_path):
+    """Two files back to back through the CLI entry (config-4 style), -c flag:
+    only the clahe PNGs appear; the resident stack of file 1 is released."""
+    from solex_ser_recon_en_b200 import SHG_MAIN
+    os.environ['SHG_NO_CONFIG'] = '1'
+    a = case_file('ser16_rot', tmp_path)
+    b = case_file('ser8_rot_flip', tmp_path)
+    SHG_MAIN.options['output_dir'] = str(tmp_path)
+    try:
+        assert SHG_MAIN.main(['-cw0,2', a, b]) == 0
+    finally:
+        SHG_MAIN.options['output_dir'] = ''
+    names = set(os.listdir(str(tmp_path)))
+    for base in ('ser16_rot', 'ser8_rot_flip'):
+        for sh in (0, 2):
+            assert f'{base}_shift={sh}_clahe.png' in names
+            assert f'{base}_shift={sh}_protus.png' not in names
+        assert f'{base}_log.txt' in names
+
+
+def test_bad_file_raises_like_reference(tmp_path):
+    from solex_ser_recon_en_b200 import Solex_recon
+    bad = os.path.join(str(tmp_path), 'scan.txt')
+    open(bad, 'w').write('x')
+    with pytest.raises(Exception, match='neither is SER nor AVI'):
+        Solex_recon.solex_read(bad, options_for('ser16_rot', tmp_path))
+
+
+def test_reader_on_host_frames(tmp_path):
+    """compute_mean_return_fit / read_video_improved accept the reference-style
+    all_video_reader (oriented frames in RAM) as the spectral analyser uses them."""
+    from solex_ser_recon_en_b200 import solex_util, video_reader
+    g = golden('ser16_rot')
+    path = case_file('ser16_rot', tmp_path)
+    rdr = video_reader.all_video_reader(path)
+    opt = options_for('ser16_rot', tmp_path, _nolog=True)
+    opt['shift'] = [int(s) for s in g['shift']]
+    mean_img, fit, y1, y2 = solex_util.compute_mean_return_fit(rdr, opt, {}, rdr.iw, rdr.ih, os.path.splitext(path)[0])
+    assert np.array_equal(mean_img, g['mean_img']) and (y1, y2) == (int(g['y1']), int(g['y2']))
+    np.testing.assert_allclose(fit, g['fit'], rtol=0, atol=1e-7)
+    rdr.reset()
+    disks, ih, iw, n = solex_util.read_video_improved(rdr, fit, opt)
+    assert (ih, iw, n) == (int(g['ih']), int(g['iw']), int(g['n']))
+    for i, d in enumerate(disks):
+        assert np.array_equal(np.asarray(d), g[f'disk{i}'])
