@@ -105,18 +105,25 @@ int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, i
  * output's fastest axis (r' = rows-1-r): frame-major disk -> reference (ih, N)
  * layout, with the reference's flip_x (Solex_recon.py:75-76) fused. */
 int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t cols, uint16_t* d_out, int flip, void* stream);
-/* d_out[0]=min, d_out[1]=max of n uint16 values (d_out must be preset to {65535,0}) */
-int shg_minmax_u16(const uint16_t* d_in, int64_t n, uint32_t* d_out2, void* stream);
+/* Batched min / max: image j (j < n_imgs) starts at d_in + (d_sel ? d_sel[j] : j)*img_stride
+ * and has n uint16 values; d_out[2j] = min, d_out[2j+1] = max (initialised here). */
+int shg_minmax_u16(const uint16_t* d_in, int64_t n, int64_t img_stride, const int32_t* d_sel, int n_imgs,
+                   uint32_t* d_out, void* stream);
 
 /* ---- a10: circularisation warp (reference ellipse_to_circle.py:94-118) -- */
-/* Per-row 1-D linear resample of a frame-major disk (n_frames x ih):
+/* Per-row 1-D linear resample of frame-major disks (n_frames x ih each), batched
+ * over n_imgs images that share the geometry (every shift of one scan):
  *   x = (m00*c + m01*r) + m02; out[r][c] = trunc(clip((1-d)*in[floor x][r] + d*in[ceil x][r]))
- * taps outside [0,n_frames) (or rows >= ih) read cval; clip to [lo,hi] as
- * skimage.transform.warp does; output row-major (out_rows x out_cols).
- * flip != 0 reads the disk with its frame axis reversed (flip_x). */
-int shg_warp_rows(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
-                  double m00, double m01, double m02, double cval, double lo, double hi,
-                  uint16_t* d_out, int out_rows, int out_cols, void* stream);
+ * taps outside [0,n_frames) (or rows >= ih) read cval = image[0][0]; the clip
+ * range [lo,hi] = the image's min / max as skimage.transform.warp uses it, read
+ * from d_minmax (shg_minmax_u16 output, stays on the device).  Image j is
+ * d_disk + (d_sel ? d_sel[j] : j)*disk_stride; output j is row-major
+ * (out_rows x out_cols) at d_out + j*out_stride.  flip != 0 reads the disks with
+ * their frame axis reversed (the reference's flip_x). */
+int shg_warp_rows(const uint16_t* d_disk, int64_t disk_stride, const int32_t* d_sel, int n_imgs,
+                  int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
+                  const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows, int out_cols,
+                  void* stream);
 
 /* ---- a11 helper: 4x4 block sums (reference ellipse_to_circle.py:301) ---- */
 /* downscale_local_mean numerator: out[ri][ci] = sum of the 4x4 block of the
@@ -124,24 +131,60 @@ int shg_warp_rows(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
 int shg_downscale4_sum(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
                        uint32_t* d_out, int out_rows, int out_cols, void* stream);
 
+/* ---- a11: limb detection for the ellipse fit (reference ellipse_to_circle.py:148-250)
+ * Works on the integer 4x4 block sums S of shg_downscale4_sum (the reference's
+ * downscaled image/65536 is S * 2^-20 exactly).  See csrc/limb.cu for how each
+ * step mirrors cv2.blur / np.percentile / np.histogram / scipy.ndimage /
+ * skimage.feature.canny operation order. */
+/* exact box sums, BORDER_REFLECT_101, anchor k/2 (cv2.blur on CV_64F before its scale) */
+int shg_box_sum_u32(const uint32_t* d_in, int rows, int cols, int kw, int kh, uint32_t* d_out,
+                    uint32_t* d_tmp, void* stream);
+int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, void* stream);
+/* exact order statistics: h_out[q] = the h_ranks[q]-th smallest (0-based) of d_vals.
+ * Blocking (reads four 256-bin histograms back per rank).  d_work256: 256 uint32. */
+int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
+                   uint32_t* h_out, uint32_t* d_work256, void* stream);
+/* blurred = (B * 2^-20) * scale.  d_out2 = {min B, max B} over pixels with blurred < ceiling */
+int shg_blur_range(const uint32_t* d_box, int64_t n, double scale, double ceiling, uint32_t* d_out2, void* stream);
+/* np.histogram(blurred[blurred < ceiling], bins=n_bins) given its n_bins+1 edges; d_counts: 32 uint64 */
+int shg_blur_hist(const uint32_t* d_box, int64_t n, double scale, double ceiling, const double* h_edges,
+                  int n_bins, uint64_t* d_counts, void* stream);
+/* flood = blurred < level ? 0 : 65000;  smoothed = gaussian(flood) / (gaussian(ones) + eps),
+ * scipy.ndimage.gaussian_filter order (axis 0 then 1, mode constant); h_weights[k] = weight at
+ * offset k (0..radius).  d_tmp2: two rows*cols double images. */
+int shg_flood_smooth(const uint32_t* d_box, int rows, int cols, double scale, double level,
+                     const double* h_weights, int radius, double eps, double* d_smoothed,
+                     double* d_tmp2, void* stream);
+/* scipy.ndimage.sobel along axis 0 (d_gi) and axis 1 (d_gj), mode reflect, and sqrt(gi*gi + gj*gj) */
+int shg_sobel_mag(const double* d_smoothed, int rows, int cols, double* d_gi, double* d_gj, double* d_mag,
+                  void* stream);
+/* skimage canny's interpolated non-maximum suppression: pixels with mag >= low that are local maxima
+ * along the gradient are appended (unordered) to d_list_idx (flat index) / d_list_mag; *d_count may
+ * exceed cap, in which case the list is truncated and the caller retries with a larger cap. */
+int shg_nms_candidates(const double* d_gi, const double* d_gj, const double* d_mag, int rows, int cols,
+                       double low, uint32_t* d_count, uint32_t cap, uint32_t* d_list_idx,
+                       double* d_list_mag, void* stream);
+
 /* ---- a12: transversalium (reference solex_util.py:76-86,383-395,489-516) */
 /* tab[v] = log(v) for v in [0, 65536) (tab[0] = -inf): pixels are uint16, so
  * the reference's log(img[y]/img[y-1]) is tab[a] - tab[b] to ~2e-15 absolute. */
 int shg_log_table(double* d_tab65536, void* stream);
-/* For each listed row y (rows[j]), over columns [xa[j], xb[j]):
- *   rat = log(img[y][x] / img[y-1][x]);  out[j] = mean(rat[|rat-med|/MAD < 2])
+/* For each listed row y (rows[j]) of each of n_imgs images (image i at
+ * d_img + i*img_stride), over columns [xa[j], xb[j]):
+ *   rat = log(img[y][x] / img[y-1][x]);  out[i*n_list + j] = mean(rat[|rat-med|/MAD < 2])
  * (median / MAD as np.median; MAD == 0 keeps all; an empty chord or a nan
- * gives nan as in the reference).  One CTA per row, exact order statistics by
- * radix select in shared memory.  max_len = max(xb-xa).  Chords longer than
- * shared memory holds use d_work (shg_transv_workspace_bytes; 0 = not needed). */
-int64_t shg_transv_workspace_bytes(int n_list, int max_len);
-int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols,
+ * gives nan as in the reference).  One CTA per (row, image), exact order
+ * statistics by radix select in shared memory.  max_len = max(xb-xa).  Chords
+ * longer than shared memory holds use d_work (shg_transv_workspace_bytes; 0 =
+ * not needed). */
+int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs);
+int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
                          const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,
                          int max_len, const double* d_logtab, double* d_out,
                          void* d_work, int64_t work_bytes, void* stream);
-/* out[r][c] = trunc(min(img[r][c] * gain[r], 65535)) */
-int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, const double* d_gain,
-                      uint16_t* d_out, void* stream);
+/* out[i][r][c] = trunc(min(img[i][r][c] * gain[i][r], 65535)), images at stride img_stride */
+int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
+                      const double* d_gain, uint16_t* d_out, void* stream);
 
 /* ---- a1/a2: ingest (reference video_reader.py:94-123) ------------------- */
 /* Streams frames of a file into a device-resident stack through a ring of

@@ -40,13 +40,21 @@ _PROTOS = {
     'shg_recon_workspace_bytes': (i64, [i32, i32]),
     'shg_recon': (i32, [vp, i32, i64, i32, i32, vp, vp, i32, vp, i64, i64, i32, vp, i64, vp]),
     'shg_transpose_u16': (i32, [vp, i64, i64, vp, i32, vp]),
-    'shg_minmax_u16': (i32, [vp, i64, vp, vp]),
-    'shg_warp_rows': (i32, [vp, i64, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp, i32, i32, vp]),
+    'shg_minmax_u16': (i32, [vp, i64, i64, vp, i32, vp, vp]),
+    'shg_warp_rows': (i32, [vp, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp]),
     'shg_downscale4_sum': (i32, [vp, i64, i32, i32, vp, i32, i32, vp]),
+    'shg_box_sum_u32': (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    'shg_sum_u32': (i32, [vp, i64, vp, vp]),
+    'shg_select_u32': (i32, [vp, i64, C.POINTER(i64), i32, C.POINTER(C.c_uint32), vp, vp]),
+    'shg_blur_range': (i32, [vp, i64, dbl, dbl, vp, vp]),
+    'shg_blur_hist': (i32, [vp, i64, dbl, dbl, C.POINTER(dbl), i32, vp, vp]),
+    'shg_flood_smooth': (i32, [vp, i32, i32, dbl, dbl, C.POINTER(dbl), i32, dbl, vp, vp, vp]),
+    'shg_sobel_mag': (i32, [vp, i32, i32, vp, vp, vp, vp]),
+    'shg_nms_candidates': (i32, [vp, vp, vp, i32, i32, dbl, vp, C.c_uint32, vp, vp, vp]),
     'shg_log_table': (i32, [vp, vp]),
-    'shg_transv_workspace_bytes': (i64, [i32, i32]),
-    'shg_transv_row_stats': (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]),
-    'shg_row_scale_u16': (i32, [vp, i32, i32, vp, vp, vp]),
+    'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),
+    'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]),
+    'shg_row_scale_u16': (i32, [vp, i32, i32, i32, i64, vp, vp, vp]),
     'shg_ingest_create': (i32, [i32, i64, i32, i32, C.POINTER(vp)]),
     'shg_ingest_destroy': (i32, [vp]),
     'shg_ingest_file': (i32, [vp, C.c_char_p, i64, i64, i64, i64, i64, vp, i32, vp, vp, C.POINTER(dbl)]),

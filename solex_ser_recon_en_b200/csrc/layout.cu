@@ -52,8 +52,12 @@ transpose_u16_kernel(const uint16_t* __restrict__ in, int64_t rows, int64_t cols
     }
 }
 
+// min / max of every image of a batch (blockIdx.y = image)
 __global__ void __launch_bounds__(256)
-minmax_u16_kernel(const uint16_t* __restrict__ in, int64_t n, unsigned int* __restrict__ out2) {
+minmax_u16_kernel(const uint16_t* __restrict__ base, int64_t n, int64_t img_stride, const int32_t* __restrict__ sel,
+                  unsigned int* __restrict__ out /* [n_imgs][2], preset to {65535, 0} */) {
+    const uint16_t* in = base + (int64_t)(sel ? sel[blockIdx.y] : blockIdx.y) * img_stride;
+    unsigned int* out2 = out + 2 * blockIdx.y;
     unsigned int lo = 0xffffu, hi = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,6 +83,11 @@ minmax_u16_kernel(const uint16_t* __restrict__ in, int64_t n, unsigned int* __re
     }
 }
 
+__global__ void minmax_init_kernel(unsigned int* out, int n_imgs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_imgs) { out[2 * i] = 0xffffu; out[2 * i + 1] = 0; }
+}
+
 }  // namespace
 
 extern "C" int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t cols, uint16_t* d_out, int flip,
@@ -92,10 +101,16 @@ extern "C" int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t col
     return 0;
 }
 
-extern "C" int shg_minmax_u16(const uint16_t* d_in, int64_t n, uint32_t* d_out2, void* stream) {
-    if (n <= 0) return 0;
-    const int64_t blocks = std::min<int64_t>(ceil_div64(n, 256 * 8), (int64_t)SHG_SM_COUNT_B200 * 8);
-    minmax_u16_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, as_stream(stream)>>>(d_in, n, d_out2);
+extern "C" int shg_minmax_u16(const uint16_t* d_in, int64_t n, int64_t img_stride, const int32_t* d_sel, int n_imgs,
+                              uint32_t* d_out, void* stream) {
+    if (n <= 0 || n_imgs <= 0) return 0;
+    SHG_REQUIRE(n_imgs <= 65535, "shg_minmax_u16: too many images");
+    cudaStream_t st = as_stream(stream);
+    minmax_init_kernel<<<(n_imgs + 255) / 256, 256, 0, st>>>(d_out, n_imgs);
+    SHG_LAUNCH_CHECK();
+    const int64_t want = std::max<int64_t>(1, (int64_t)SHG_SM_COUNT_B200 * 8 / n_imgs);
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256 * 8), std::max<int64_t>(want, 8)));
+    minmax_u16_kernel<<<dim3((unsigned)blocks, n_imgs), 256, 0, st>>>(d_in, n, img_stride, d_sel, d_out);
     SHG_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,328 @@
+// Limb detection front end of the ellipse fit, on the 4x-downscaled disk image
+// (reference ellipse_to_circle.py:148-228 get_flood_image, :231-250 the Canny
+// call of get_edge_list).  The image is kept as the integer 4x4 block sums S
+// (value = S * 2^-20 of the reference's image/65536), which makes OpenCV's
+// double-precision box filter exact in integers; every floating-point step
+// below reproduces the operation ORDER of the library routine the reference
+// calls, so thresholds and tie-breaks come out the same:
+//   cv2.blur (CV_64F)            exact window sum, one multiply by 1/(kw*kh)
+//   np.percentile / np.median    exact order statistics by radix select on the integer sums
+//   np.histogram (20 uniform bins)  bin = the edge interval that contains the value
+//   scipy.ndimage.gaussian_filter   NI_Correlate1D symmetric form: in[0]*w[0] + sum_{j=-r..-1} (in[j]+in[-j])*w[j]
+//   scipy.ndimage.sobel          (in[-1]-in[+1])*(-1) then in[0]*2 + (in[-1]+in[+1])*1, mode 'reflect'
+//   skimage.feature.canny        magnitude, interpolated non-maximum suppression (_canny_cy)
+// Outputs are tiny (order statistics, 20 counts, a list of thin-edge pixels);
+// labelling, convex hull and the 6-parameter ellipse fit stay on the host.
+// All kernels are O(rows*cols) over a ~5 Mpx image: microseconds each.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+__device__ __forceinline__ int reflect_edge(int i, int n) {      // scipy 'reflect': d c b a | a b c d | d c b a
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256)
+hsum_u32_kernel(const uint32_t* __restrict__ img, int rows, int cols, int kw, uint32_t* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    const uint32_t* row = img + (int64_t)r * cols;
+    const int a = c - kw / 2;
+    uint32_t s = 0;
+    for (int t = 0; t < kw; ++t) s += row[reflect101(a + t, cols)];
+    out[idx] = s;
+}
+
+__global__ void __launch_bounds__(256)
+vsum_u32_kernel(const uint32_t* __restrict__ hs, int rows, int cols, int kh, uint32_t* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    const int a = r - kh / 2;
+    uint32_t s = 0;
+    for (int t = 0; t < kh; ++t) s += hs[(int64_t)reflect101(a + t, rows) * cols + c];
+    out[idx] = s;
+}
+
+__global__ void __launch_bounds__(256)
+sum_u32_kernel(const uint32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += v[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// histogram of byte `shift/8` of the keys whose bits above it equal `prefix`
+__global__ void __launch_bounds__(256)
+radix_hist_kernel(const uint32_t* __restrict__ v, int64_t n, uint32_t prefix, int shift, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int hi_shift = shift + 8;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const uint32_t k = v[i];
+        if (hi_shift >= 32 || (k >> hi_shift) == prefix) atomicAdd(&h[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// blurred(B) = (B * 2^-20) * scale, exactly as cv2.blur computes it from image/65536
+__device__ __forceinline__ double blurred_of(uint32_t b, double scale) {
+    return __dmul_rn(__dmul_rn((double)b, 9.5367431640625e-07), scale);
+}
+
+// out[0] = min B, out[1] = max B among pixels whose blurred value is < ceiling
+__global__ void __launch_bounds__(256)
+blur_range_kernel(const uint32_t* __restrict__ box, int64_t n, double scale, double ceiling, unsigned int* __restrict__ out) {
+    unsigned int lo = 0xffffffffu, hi = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const uint32_t b = box[i];
+        if (blurred_of(b, scale) < ceiling) { lo = min(lo, b); hi = max(hi, b); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, lo); atomicMax(out + 1, hi); }
+}
+
+struct Edges { double e[33]; int n_bins; };
+
+__global__ void __launch_bounds__(256)
+blur_hist_kernel(const uint32_t* __restrict__ box, int64_t n, double scale, double ceiling, const Edges ed,
+                 unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int h[32];
+    if (threadIdx.x < 32) h[threadIdx.x] = 0;
+    __syncthreads();
+    const double first = ed.e[0], last = ed.e[ed.n_bins];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double x = blurred_of(box[i], scale);
+        if (!(x < ceiling) || x < first || x > last) continue;
+        int b = 0;                                              // edges[b] <= x < edges[b+1]; last bin closed
+        for (int j = 1; j < ed.n_bins; ++j) b += x >= ed.e[j] ? 1 : 0;
+        atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+struct GaussW { double w[33]; int radius; };                   // w[k] = weight at offset -k (symmetric)
+
+// gaussian along `axis` of either the flood image made on the fly from the box
+// sums (src == nullptr) or a double image; mode 'constant' (zeros outside)
+template <bool FROM_BOX>
+__global__ void __launch_bounds__(256)
+gauss1d_kernel(const uint32_t* __restrict__ box, double scale, double level, int ones,
+               const double* __restrict__ src, int rows, int cols, int axis, const GaussW g, double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    auto at = [&](int rr, int cc) -> double {
+        if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) return 0.0;
+        if (FROM_BOX) {
+            if (ones) return 1.0;
+            return blurred_of(box[(int64_t)rr * cols + cc], scale) < level ? 0.0 : 65000.0;
+        }
+        return src[(int64_t)rr * cols + cc];
+    };
+    const int dr = axis == 0 ? 1 : 0, dc = axis == 0 ? 0 : 1;
+    double acc = __dmul_rn(at(r, c), g.w[0]);
+    for (int k = g.radius; k >= 1; --k) {                       // j = -radius .. -1
+        const double pair = __dadd_rn(at(r - k * dr, c - k * dc), at(r + k * dr, c + k * dc));
+        acc = __dadd_rn(acc, __dmul_rn(pair, g.w[k]));
+    }
+    out[idx] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+divide_kernel(double* __restrict__ num, const double* __restrict__ den, double eps, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) num[i] = __ddiv_rn(num[i], __dadd_rn(den[i], eps));
+}
+
+// scipy.ndimage.sobel along both axes + magnitude
+__global__ void __launch_bounds__(256)
+sobel_kernel(const double* __restrict__ s, int rows, int cols, double* __restrict__ gi, double* __restrict__ gj,
+             double* __restrict__ mag) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    auto S = [&](int rr, int cc) { return s[(int64_t)reflect_edge(rr, rows) * cols + reflect_edge(cc, cols)]; };
+    // derivative: in[0]*0 + (in[-1] - in[+1]) * (-1)
+    auto d1 = [&](int rr, int cc) {                              // along axis 1 (columns)
+        return __dadd_rn(__dmul_rn(S(rr, cc), 0.0), __dmul_rn(__dsub_rn(S(rr, cc - 1), S(rr, cc + 1)), -1.0));
+    };
+    auto d0 = [&](int rr, int cc) {                              // along axis 0 (rows)
+        return __dadd_rn(__dmul_rn(S(rr, cc), 0.0), __dmul_rn(__dsub_rn(S(rr - 1, cc), S(rr + 1, cc)), -1.0));
+    };
+    // the derivative image is itself extended by reflection before the [1,2,1] pass
+    auto D1 = [&](int rr, int cc) { return d1(reflect_edge(rr, rows), reflect_edge(cc, cols)); };
+    auto D0 = [&](int rr, int cc) { return d0(reflect_edge(rr, rows), reflect_edge(cc, cols)); };
+    // smoothing: in[0]*2 + (in[-1] + in[+1]) * 1
+    const double j = __dadd_rn(__dmul_rn(D1(r, c), 2.0), __dmul_rn(__dadd_rn(D1(r - 1, c), D1(r + 1, c)), 1.0));
+    const double i = __dadd_rn(__dmul_rn(D0(r, c), 2.0), __dmul_rn(__dadd_rn(D0(r, c - 1), D0(r, c + 1)), 1.0));
+    gi[idx] = i;
+    gj[idx] = j;
+    mag[idx] = __dsqrt_rn(__dadd_rn(__dmul_rn(i, i), __dmul_rn(j, j)));
+}
+
+// interpolated non-maximum suppression; survivors are appended to a list
+__global__ void __launch_bounds__(256)
+nms_kernel(const double* __restrict__ gi, const double* __restrict__ gj, const double* __restrict__ mag, int rows,
+           int cols, double low, unsigned int* __restrict__ count, unsigned int cap, uint32_t* __restrict__ list_idx,
+           double* __restrict__ list_mag) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    if (r < 1 || r >= rows - 1 || c < 1 || c >= cols - 1) return;          // eroded mask
+    const double m = mag[idx];
+    if (!(m >= low)) return;
+    const double a = gi[idx], b = gj[idx];
+    const double aa = fabs(a), ab = fabs(b);
+    const bool same = (a >= 0 && b >= 0) || (a <= 0 && b <= 0);
+    const bool opp = (a <= 0 && b >= 0) || (a >= 0 && b <= 0);
+    if (!(same || opp)) return;                                             // nan gradients
+    int d1i, d1j, d2i, d2j;
+    double w;
+    if (same) {
+        if (aa > ab) { d1i = 1; d1j = 0; d2i = 1; d2j = 1; w = __ddiv_rn(ab, aa); }
+        else         { d1i = 0; d1j = 1; d2i = 1; d2j = 1; w = __ddiv_rn(aa, ab); }
+    } else {
+        if (aa < ab) { d1i = 0; d1j = 1; d2i = -1; d2j = 1; w = __ddiv_rn(aa, ab); }
+        else         { d1i = -1; d1j = 0; d2i = -1; d2j = 1; w = __ddiv_rn(ab, aa); }
+    }
+    auto M = [&](int di, int dj) { return mag[(int64_t)(r + di) * cols + (c + dj)]; };
+    const double omw = __dsub_rn(1.0, w);
+    const double plus = __dadd_rn(__dmul_rn(M(d2i, d2j), w), __dmul_rn(M(d1i, d1j), omw));
+    const double minus = __dadd_rn(__dmul_rn(M(-d2i, -d2j), w), __dmul_rn(M(-d1i, -d1j), omw));
+    if (plus <= m && minus <= m && m > 0.0) {
+        const unsigned int slot = atomicAdd(count, 1u);
+        if (slot < cap) { list_idx[slot] = (uint32_t)idx; list_mag[slot] = m; }
+    }
+}
+
+unsigned grid_for(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256), 148 * 16)); }
+
+}  // namespace
+
+extern "C" int shg_box_sum_u32(const uint32_t* d_in, int rows, int cols, int kw, int kh, uint32_t* d_out,
+                               uint32_t* d_tmp, void* stream) {
+    SHG_REQUIRE(kw >= 1 && kh >= 1 && kw <= cols && kh <= rows, "shg_box_sum_u32: kernel %dx%d does not fit %dx%d", kw,
+                kh, cols, rows);
+    SHG_REQUIRE((int64_t)kw * kh * (16LL * 65535) < 0xffffffffLL, "shg_box_sum_u32: window too large for 32-bit sums");
+    const int64_t n = (int64_t)rows * cols;
+    const unsigned blocks = (unsigned)ceil_div64(n, 256);
+    hsum_u32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_in, rows, cols, kw, d_tmp);
+    vsum_u32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_tmp, rows, cols, kh, d_out);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, void* stream) {
+    SHG_CHECK(cudaMemsetAsync(d_out, 0, 8, as_stream(stream)));
+    sum_u32_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(d_in, n, reinterpret_cast<unsigned long long*>(d_out));
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
+                              uint32_t* h_out, uint32_t* d_work256, void* stream) {
+    SHG_REQUIRE(n > 0 && n_ranks >= 0, "shg_select_u32: empty input");
+    cudaStream_t st = as_stream(stream);
+    unsigned int hist[256];
+    for (int q = 0; q < n_ranks; ++q) {
+        int64_t rank = h_ranks[q];
+        SHG_REQUIRE(rank >= 0 && rank < n, "shg_select_u32: rank %lld out of range", (long long)rank);
+        uint32_t prefix = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            SHG_CHECK(cudaMemsetAsync(d_work256, 0, 256 * 4, st));
+            radix_hist_kernel<<<grid_for(n), 256, 0, st>>>(d_vals, n, prefix, shift, d_work256);
+            SHG_LAUNCH_CHECK();
+            SHG_CHECK(cudaMemcpyAsync(hist, d_work256, 256 * 4, cudaMemcpyDeviceToHost, st));
+            SHG_CHECK(cudaStreamSynchronize(st));
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (rank < (int64_t)hist[b]) break;
+                rank -= hist[b];
+            }
+            SHG_REQUIRE(b < 256, "shg_select_u32: internal error (histogram does not cover the rank)");
+            prefix = (prefix << 8) | (uint32_t)b;
+        }
+        h_out[q] = prefix;
+    }
+    return 0;
+}
+
+extern "C" int shg_blur_range(const uint32_t* d_box, int64_t n, double scale, double ceiling, uint32_t* d_out2,
+                              void* stream) {
+    const unsigned int init[2] = {0xffffffffu, 0u};
+    SHG_CHECK(cudaMemcpyAsync(d_out2, init, 8, cudaMemcpyHostToDevice, as_stream(stream)));
+    blur_range_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(d_box, n, scale, ceiling, d_out2);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_blur_hist(const uint32_t* d_box, int64_t n, double scale, double ceiling, const double* h_edges,
+                             int n_bins, uint64_t* d_counts, void* stream) {
+    SHG_REQUIRE(n_bins >= 1 && n_bins <= 32, "shg_blur_hist: 1..32 bins");
+    Edges ed;
+    for (int i = 0; i <= n_bins; ++i) ed.e[i] = h_edges[i];
+    ed.n_bins = n_bins;
+    SHG_CHECK(cudaMemsetAsync(d_counts, 0, 32 * 8, as_stream(stream)));
+    blur_hist_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(d_box, n, scale, ceiling, ed,
+                                                               reinterpret_cast<unsigned long long*>(d_counts));
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_flood_smooth(const uint32_t* d_box, int rows, int cols, double scale, double level,
+                                const double* h_weights, int radius, double eps, double* d_smoothed,
+                                double* d_tmp2 /* 2 images */, void* stream) {
+    SHG_REQUIRE(radius >= 0 && radius <= 32, "shg_flood_smooth: radius %d (max 32)", radius);
+    GaussW g;
+    for (int k = 0; k <= radius; ++k) g.w[k] = h_weights[k];
+    g.radius = radius;
+    const int64_t n = (int64_t)rows * cols;
+    const unsigned blocks = (unsigned)ceil_div64(n, 256);
+    cudaStream_t st = as_stream(stream);
+    double* t0 = d_tmp2;
+    double* t1 = d_tmp2 + n;
+    // gaussian of the all-ones mask (the "bleed over" normalisation)
+    gauss1d_kernel<true><<<blocks, 256, 0, st>>>(d_box, scale, level, 1, nullptr, rows, cols, 0, g, t0);
+    gauss1d_kernel<false><<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, t0, rows, cols, 1, g, t1);
+    // gaussian of the flood image
+    gauss1d_kernel<true><<<blocks, 256, 0, st>>>(d_box, scale, level, 0, nullptr, rows, cols, 0, g, t0);
+    gauss1d_kernel<false><<<blocks, 256, 0, st>>>(nullptr, 0, 0, 0, t0, rows, cols, 1, g, d_smoothed);
+    divide_kernel<<<blocks, 256, 0, st>>>(d_smoothed, t1, eps, n);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_sobel_mag(const double* d_smoothed, int rows, int cols, double* d_gi, double* d_gj, double* d_mag,
+                             void* stream) {
+    const int64_t n = (int64_t)rows * cols;
+    sobel_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(d_smoothed, rows, cols, d_gi, d_gj, d_mag);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_nms_candidates(const double* d_gi, const double* d_gj, const double* d_mag, int rows, int cols,
+                                  double low, uint32_t* d_count, uint32_t cap, uint32_t* d_list_idx,
+                                  double* d_list_mag, void* stream) {
+    const int64_t n = (int64_t)rows * cols;
+    SHG_CHECK(cudaMemsetAsync(d_count, 0, 4, as_stream(stream)));
+    nms_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(d_gi, d_gj, d_mag, rows, cols, low, d_count,
+                                                                          cap, d_list_idx, d_list_mag);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}

@@ -19,8 +19,7 @@
 
 namespace {
 
-constexpr int kT = 1024;
-constexpr int kListCap = 256;
+constexpr int kListCap = 256;            // upper bound; a CTA of T threads ranks at most min(T, 256) candidates
 constexpr double kQ = 1073741824.0;     // 2^30
 
 struct Shared {
@@ -55,8 +54,9 @@ __device__ void block_minmax(double& mn, double& mx, Shared& S) {
     __syncthreads();
     if (lane == 0) { S.red[0][warp] = mn; S.red[1][warp] = mx; }
     __syncthreads();
-    mn = warp_min(S.red[0][lane]);
-    mx = warp_max(S.red[1][lane]);
+    const int nw = blockDim.x >> 5;
+    mn = warp_min(lane < nw ? S.red[0][lane] : INFINITY);
+    mx = warp_max(lane < nw ? S.red[1][lane] : -INFINITY);
 }
 
 __device__ void block_sum2(double& a, double& b, Shared& S) {
@@ -66,8 +66,9 @@ __device__ void block_sum2(double& a, double& b, Shared& S) {
     __syncthreads();
     if (lane == 0) { S.red[0][warp] = a; S.red[1][warp] = b; }
     __syncthreads();
-    a = warp_sum(S.red[0][lane]);
-    b = warp_sum(S.red[1][lane]);
+    const int nw = blockDim.x >> 5;
+    a = warp_sum(lane < nw ? S.red[0][lane] : 0.0);
+    b = warp_sum(lane < nw ? S.red[1][lane] : 0.0);
 }
 
 template <int KIND>
@@ -85,7 +86,7 @@ __device__ __forceinline__ uint32_t qkey(double x, double lo, double scale) {
 // Exact order statistics t (and t+1 when need2) of the keys that lie in the
 // finite range [lo, hi]; m = number of such keys; 0 <= t (< t+1) < m.
 // Results in S.dbc[0], S.dbc[1].
-template <int KIND>
+template <int KIND, int kT>
 __device__ void block_select(const double* vals, int n, double med, double lo, double hi, int m, int t, bool need2,
                              Shared& S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -99,7 +100,8 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
         if (!(scale < 1e300)) scale = 1e300;
         uint32_t prefix = 0;
         int level = 0;
-        for (; level < 6 && m > kListCap; ++level) {
+        constexpr int kCap = kT < kListCap ? kT : kListCap;
+        for (; level < 6 && m > kCap; ++level) {
             const int pshift = 30 - 5 * level, bshift = 25 - 5 * level;
             unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // 32 bins x 8-bit fields ... widened below
             // per-thread counts can exceed 255 for very long rows: flush in chunks of 255 elements
@@ -182,7 +184,7 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
             prefix = (prefix << 5) | (uint32_t)b0;
         }
         const int pshift = 30 - 5 * level;
-        if (m <= kListCap) {
+        if (m <= kCap) {
             if (threadIdx.x == 0) S.list_n = 0;
             __syncthreads();
             for (int i = threadIdx.x; i < n; i += kT) {
@@ -191,12 +193,12 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
                     const uint32_t q = qkey(x, lo, scale);
                     if (level == 0 || (q >> pshift) == prefix) {
                         const int slot = atomicAdd(&S.list_n, 1);
-                        if (slot < kListCap) S.list[slot] = x;
+                        if (slot < kCap) S.list[slot] = x;
                     }
                 }
             }
             __syncthreads();
-            const int mm = min(S.list_n, kListCap);
+            const int mm = min(S.list_n, kCap);
             if ((int)threadIdx.x < mm) {
                 const double c = S.list[threadIdx.x];
                 int rank = 0;
@@ -228,27 +230,27 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
 }
 
 // value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
-template <int KIND>
+template <int KIND, int kT>
 __device__ void ranked_pair(const double* vals, int n, double med, double lo, double hi, int nneg, int nfin,
                             int t0, int t1, double& v0, double& v1, Shared& S) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
     if (g0 == 0 && g1 == 0) {
-        block_select<KIND>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
         v0 = S.dbc[0];
         v1 = S.dbc[1];
         __syncthreads();
         return;
     }
     if (g0 == 0) {
-        block_select<KIND>(vals, n, med, lo, hi, nfin, t0 - nneg, false, S);
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, false, S);
         v0 = S.dbc[0];
         __syncthreads();
     } else {
         v0 = g0 < 0 ? -INFINITY : INFINITY;
     }
     if (g1 == 0) {
-        block_select<KIND>(vals, n, med, lo, hi, nfin, t1 - nneg, false, S);
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t1 - nneg, false, S);
         v1 = S.dbc[0];
         __syncthreads();
     } else {
@@ -256,22 +258,26 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
     }
 }
 
+template <int kT>
 __global__ void __launch_bounds__(kT)
-transv_row_stats_kernel(const uint16_t* __restrict__ img, int cols, const int32_t* __restrict__ rows,
-                        const int32_t* __restrict__ xa_list, const int32_t* __restrict__ xb_list,
+transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
+                        const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
+                        const int32_t* __restrict__ xb_list, int n_list,
                         const double* __restrict__ logtab, double* __restrict__ out,
                         double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     double* vals = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
     const int j = blockIdx.x;
+    const int64_t slot = (int64_t)blockIdx.y * n_list + j;          // (image, row) result index
+    const uint16_t* img = img_base + (int64_t)blockIdx.y * img_stride;
     const int y = rows[j], xa = xa_list[j], xb = xb_list[j];
     const int n = xb - xa;
     if (n <= 0) {                                   // np.mean of an empty slice
-        if (threadIdx.x == 0) out[j] = NAN;
+        if (threadIdx.x == 0) out[slot] = NAN;
         return;
     }
-    if (n > smem_cap) vals = gscratch + (int64_t)j * scratch_pitch;
+    if (n > smem_cap) vals = gscratch + slot * scratch_pitch;
     const uint16_t* ry = img + (int64_t)y * cols + xa;
     const uint16_t* rp = img + (int64_t)(y - 1) * cols + xa;
 
@@ -298,28 +304,28 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img, int cols, const int32_
             if (c) atomicAdd(&S.cnt[2], (unsigned long long)c);
         }
     }
-    block_minmax(fmn, fmx, S);                       // also orders the smem writes of vals[]
+    block_minmax(fmn, fmx, S);                       // also orders the writes of vals[]
     __syncthreads();
     const int t_nan = (int)S.cnt[0], t_neg = (int)S.cnt[1], t_pos = (int)S.cnt[2];
     const int nfin = n - t_neg - t_pos;
     if (t_nan > 0) {                                 // np.median -> nan -> everything rejected -> mean([]) = nan
-        if (threadIdx.x == 0) out[j] = NAN;
+        if (threadIdx.x == 0) out[slot] = NAN;
         return;
     }
     // ---- median (np.median: mean of the two middle values for even n) ---------
     const int t0 = (n - 1) / 2, t1 = n / 2;
     double a0, a1;
-    ranked_pair<0>(vals, n, 0.0, fmn, fmx, t_neg, nfin, t0, t1, a0, a1, S);
+    ranked_pair<0, kT>(vals, n, 0.0, fmn, fmx, t_neg, nfin, t0, t1, a0, a1, S);
     const double med = t0 == t1 ? a0 : (a0 + a1) / 2.0;
     if (!(fabs(med) < INFINITY)) {                   // |rat - med| contains nan -> mean([]) = nan
-        if (threadIdx.x == 0) out[j] = NAN;
+        if (threadIdx.x == 0) out[slot] = NAN;
         return;
     }
     // ---- MAD -------------------------------------------------------------------
     const int ninf = t_neg + t_pos;
     double dhi = nfin > 0 ? fmax(fabs(fmn - med), fabs(fmx - med)) : 0.0;
     double b0, b1;
-    ranked_pair<1>(vals, n, med, 0.0, dhi, 0, n - ninf, t0, t1, b0, b1, S);
+    ranked_pair<1, kT>(vals, n, med, 0.0, dhi, 0, n - ninf, t0, t1, b0, b1, S);
     const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
     // ---- mean of the inliers ---------------------------------------------------
     double sum = 0.0, cnt = 0.0;
@@ -333,7 +339,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img, int cols, const int32_
         for (int i = threadIdx.x; i < n; i += kT) { sum += vals[i]; cnt += 1.0; }
     }
     block_sum2(sum, cnt, S);
-    if (threadIdx.x == 0) out[j] = sum / cnt;
+    if (threadIdx.x == 0) out[slot] = sum / cnt;
 }
 
 __global__ void __launch_bounds__(256)
@@ -343,19 +349,19 @@ log_table_kernel(double* __restrict__ tab) {
 }
 
 __global__ void __launch_bounds__(256)
-row_scale_kernel(const uint16_t* __restrict__ img, int rows, int cols, const double* __restrict__ gain,
-                 uint16_t* __restrict__ out) {
+row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int rows, int cols,
+                 const double* __restrict__ gain /* [n_imgs][rows] */, uint16_t* __restrict__ out_base) {
     const int r = blockIdx.y;
-    const double g = gain[r];
-    const uint16_t* src = img + (int64_t)r * cols;
-    uint16_t* dst = out + (int64_t)r * cols;
+    const double g = gain[(int64_t)blockIdx.z * rows + r];
+    const uint16_t* src = img_base + (int64_t)blockIdx.z * img_stride + (int64_t)r * cols;
+    uint16_t* dst = out_base + (int64_t)blockIdx.z * img_stride + (int64_t)r * cols;
     auto one = [&](uint32_t v) -> uint32_t {
         double p = __dmul_rn(u32_to_double(v), g);
         p = p > 65535.0 ? 65535.0 : p;               // ret[ret > 65535] = 65535
         p = p > 0.0 ? p : 0.0;
         return double_floor_to_u32(p) & 0xffffu;
     };
-    const bool vec = (cols % 8 == 0) && ((uintptr_t)img % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const bool vec = (cols % 8 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
     if (vec) {
         const int nv = cols / 8;
         for (int v = blockIdx.x * 256 + threadIdx.x; v < nv; v += gridDim.x * 256) {
@@ -380,51 +386,72 @@ extern "C" int shg_log_table(double* d_tab65536, void* stream) {
     return 0;
 }
 
-extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len) {
+static int transv_threads(int max_len) {
+    // enough threads that each owns <= ~32 elements, few enough that several rows share an SM
+    return max_len <= 4096 ? 128 : (max_len <= 12288 ? 512 : 1024);
+}
+
+static int64_t transv_smem_cap(int optin) {
+    return ((int64_t)optin - (int64_t)((sizeof(Shared) + 15) / 16 * 16)) / 8;
+}
+
+extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs) {
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
-    const int64_t cap = ((int64_t)optin - (int64_t)((sizeof(Shared) + 15) / 16 * 16)) / 8;
-    if (max_len <= cap) return 0;
-    return (int64_t)n_list * (((int64_t)max_len + 15) / 16 * 16) * 8;
+    if (max_len <= transv_smem_cap(optin)) return 0;
+    return (int64_t)n_imgs * n_list * (((int64_t)max_len + 15) / 16 * 16) * 8;
 }
 
-extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, const int32_t* d_rows,
-                                    const int32_t* d_xa, const int32_t* d_xb, int n_list, int max_len,
-                                    const double* d_logtab, double* d_out, void* d_work, int64_t work_bytes,
-                                    void* stream) {
+extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
+                                    const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,
+                                    int max_len, const double* d_logtab, double* d_out, void* d_work,
+                                    int64_t work_bytes, void* stream) {
     (void)rows;
-    if (n_list <= 0) return 0;
+    if (n_list <= 0 || n_imgs <= 0) return 0;
     SHG_REQUIRE(max_len >= 0 && max_len <= cols, "shg_transv_row_stats: max_len %d out of range", max_len);
+    SHG_REQUIRE(n_imgs <= 65535, "shg_transv_row_stats: too many images");
     int dev = 0, optin = 0;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int64_t head = (sizeof(Shared) + 15) / 16 * 16;
-    const int64_t cap = (optin - head) / 8;
+    const int64_t cap = transv_smem_cap(optin);
     int64_t pitch = 0;
     size_t smem = (size_t)head;
     if (max_len <= cap) {
         smem += (size_t)max_len * 8;
     } else {
         pitch = ((int64_t)max_len + 15) / 16 * 16;
-        SHG_REQUIRE(d_work && work_bytes >= (int64_t)n_list * pitch * 8,
+        SHG_REQUIRE(d_work && work_bytes >= (int64_t)n_imgs * n_list * pitch * 8,
                     "shg_transv_row_stats: chords of %d px need %lld bytes of workspace", max_len,
-                    (long long)((int64_t)n_list * pitch * 8));
+                    (long long)((int64_t)n_imgs * n_list * pitch * 8));
     }
-    SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transv_row_stats_kernel<<<n_list, kT, smem, as_stream(stream)>>>(
-        d_img, cols, d_rows, d_xa, d_xb, d_logtab, d_out, static_cast<double*>(d_work), pitch,
-        max_len <= cap ? max_len : 0);
+    const int smem_cap = max_len <= cap ? max_len : 0;
+    const dim3 grid(n_list, n_imgs);
+    cudaStream_t st = as_stream(stream);
+#define SHG_TRANSV_LAUNCH(T)                                                                                        \
+    do {                                                                                                            \
+        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       (int)smem));                                                                 \
+        transv_row_stats_kernel<T><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
+                                                          d_logtab, d_out, static_cast<double*>(d_work), pitch,     \
+                                                          smem_cap);                                                \
+    } while (0)
+    const int threads = transv_threads(max_len);
+    if (threads == 128) SHG_TRANSV_LAUNCH(128);
+    else if (threads == 512) SHG_TRANSV_LAUNCH(512);
+    else SHG_TRANSV_LAUNCH(1024);
     SHG_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, const double* d_gain, uint16_t* d_out,
-                                 void* stream) {
-    if (rows <= 0 || cols <= 0) return 0;
-    SHG_REQUIRE(rows <= 65535, "shg_row_scale_u16: too many rows");
+extern "C" int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
+                                 const double* d_gain, uint16_t* d_out, void* stream) {
+    if (rows <= 0 || cols <= 0 || n_imgs <= 0) return 0;
+    SHG_REQUIRE(rows <= 65535 && n_imgs <= 65535, "shg_row_scale_u16: too many rows / images");
     const int per_row = std::max(1, std::min(8, (cols / 8 + 255) / 256));
-    row_scale_kernel<<<dim3(per_row, rows), 256, 0, as_stream(stream)>>>(d_img, rows, cols, d_gain, d_out);
+    row_scale_kernel<<<dim3(per_row, rows, n_imgs), 256, 0, as_stream(stream)>>>(d_img, img_stride, rows, cols, d_gain,
+                                                                                d_out);
     SHG_LAUNCH_CHECK();
     return 0;
 }

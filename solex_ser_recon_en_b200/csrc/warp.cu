@@ -20,18 +20,27 @@
 namespace {
 
 constexpr int kRows = 64;      // slit rows per tile
-constexpr int kCols = 256;     // output columns per tile = threads
 constexpr int kPitch = kRows + 2;
 
-__global__ void __launch_bounds__(kCols)
-warp_rows_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, int flip,
-                 double m00, double m01, double m02, double cval, double lo, double hi,
-                 uint16_t* __restrict__ out, int out_rows, int out_cols, int span) {
+// One CTA = 64 slit rows x COLS output columns of one image (blockIdx.z).  The
+// tile width shrinks as the stretch m00 grows so that the staged frame span
+// stays ~45 KB and several CTAs per SM overlap their loads with the fp64 lerp.
+template <int COLS>
+__global__ void __launch_bounds__(256)
+warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, const int32_t* __restrict__ sel,
+                 int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
+                 const uint32_t* __restrict__ minmax /* [n_imgs][2] */,
+                 uint16_t* __restrict__ out_base, int64_t out_stride, int out_rows, int out_cols, int span) {
     extern __shared__ uint16_t tile[];           // [span][kPitch]
+    const int img = blockIdx.z;
+    const uint16_t* disk = disk_base + (int64_t)(sel ? sel[img] : img) * disk_stride;
+    uint16_t* out = out_base + (int64_t)img * out_stride;
+    const double lo = (double)minmax[2 * img], hi = (double)minmax[2 * img + 1];
+    const double cval = u32_to_double(disk[(flip ? (n_frames - 1) : 0) * (int64_t)ih]);   // image[0][0]
     const int r0 = blockIdx.y * kRows;
-    const int c0 = blockIdx.x * kCols;
+    const int c0 = blockIdx.x * COLS;
     const int r1 = min(r0 + kRows, out_rows);
-    const int c1 = min(c0 + kCols, out_cols);
+    const int c1 = min(c0 + COLS, out_cols);
     // frame range touched by this tile (x is monotone in c and in r)
     double xa = 1e300, xb = -1e300;
     {
@@ -50,8 +59,8 @@ warp_rows_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, in
     const int64_t kbase = (int64_t)floor(xa);
     const int64_t kend = min((int64_t)ceil(xb) + 1, kbase + span);   // exclusive
     const int nrow = min(r1, ih) - r0;                                // valid slit rows (may be <= 0)
-    // ---- stage: coalesced along the slit axis --------------------------------
-    for (int64_t kk = kbase + (threadIdx.x >> 5); kk < kend; kk += kCols / 32) {
+    // ---- stage: coalesced along the slit axis (64 rows = 128 B per frame) ----
+    for (int64_t kk = kbase + (threadIdx.x >> 5); kk < kend; kk += 8) {
         uint16_t* dst = tile + (kk - kbase) * kPitch;
         if (kk < 0 || kk >= n_frames) continue;                        // never read (range test below)
         const int64_t ksrc = flip ? (n_frames - 1 - kk) : kk;
@@ -67,10 +76,11 @@ warp_rows_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, in
         }
     }
     __syncthreads();
-    const int c = c0 + threadIdx.x;
+    constexpr int RGROUPS = 256 / COLS;                                // row groups working side by side
+    const int c = c0 + (threadIdx.x % COLS);
     if (c >= out_cols) return;
     const double mc = __dmul_rn(m00, (double)c);
-    for (int r = r0; r < r1; ++r) {
+    for (int r = r0 + threadIdx.x / COLS; r < r1; r += RGROUPS) {
         const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
         const double xf = floor(x), xc = ceil(x);
         const double d = __dsub_rn(x, xf);
@@ -107,22 +117,35 @@ downscale4_kernel(const uint16_t* __restrict__ disk, int64_t n_frames, int ih, i
 
 }  // namespace
 
-extern "C" int shg_warp_rows(const uint16_t* d_disk, int64_t n_frames, int ih, int flip,
-                             double m00, double m01, double m02, double cval, double lo, double hi,
-                             uint16_t* d_out, int out_rows, int out_cols, void* stream) {
-    SHG_REQUIRE(n_frames > 0 && ih > 0 && out_rows > 0 && out_cols > 0, "shg_warp_rows: bad geometry");
+extern "C" int shg_warp_rows(const uint16_t* d_disk, int64_t disk_stride, const int32_t* d_sel, int n_imgs,
+                             int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
+                             const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows,
+                             int out_cols, void* stream) {
+    SHG_REQUIRE(n_frames > 0 && ih > 0 && out_rows > 0 && out_cols > 0 && n_imgs > 0, "shg_warp_rows: bad geometry");
     SHG_REQUIRE(std::isfinite(m00) && std::isfinite(m01) && std::isfinite(m02) && m00 > 0.0,
                 "shg_warp_rows: bad matrix (%g, %g, %g)", m00, m01, m02);
-    // frames spanned by one tile: kCols columns and kRows rows, + floor/ceil taps
-    const double spanf = m00 * (kCols - 1) + std::fabs(m01) * (kRows - 1) + 4.0;
-    SHG_REQUIRE(spanf < 1500.0, "shg_warp_rows: stretch %g / shear %g too large for the tile", m00, m01);
+    SHG_REQUIRE(n_imgs <= 65535, "shg_warp_rows: too many images");
+    // frames spanned by one tile: COLS columns and kRows rows, + floor/ceil taps
+    auto span_for = [&](int cols) { return m00 * (cols - 1) + std::fabs(m01) * (kRows - 1) + 4.0; };
+    int cols = 256;
+    while (cols > 64 && span_for(cols) * kPitch * 2 > 48.0 * 1024) cols /= 2;
+    const double spanf = span_for(cols);
+    SHG_REQUIRE(spanf * kPitch * 2 < 200.0 * 1024, "shg_warp_rows: stretch %g / shear %g too large for the tile", m00,
+                m01);
     const int span = (int)std::ceil(spanf);
     const size_t smem = (size_t)span * kPitch * sizeof(uint16_t);
-    SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((out_cols + kCols - 1) / kCols, (out_rows + kRows - 1) / kRows);
+    dim3 grid((out_cols + cols - 1) / cols, (out_rows + kRows - 1) / kRows, n_imgs);
     SHG_REQUIRE(grid.y <= 65535, "shg_warp_rows: too many rows");
-    warp_rows_kernel<<<grid, kCols, smem, as_stream(stream)>>>(d_disk, n_frames, ih, flip, m00, m01, m02, cval, lo, hi,
-                                                             d_out, out_rows, out_cols, span);
+    cudaStream_t st = as_stream(stream);
+#define SHG_WARP_LAUNCH(C)                                                                                          \
+    do {                                                                                                            \
+        SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        warp_rows_kernel<C><<<grid, 256, smem, st>>>(d_disk, disk_stride, d_sel, n_frames, ih, flip, m00, m01, m02,  \
+                                                     d_minmax, d_out, out_stride, out_rows, out_cols, span);        \
+    } while (0)
+    if (cols == 256) SHG_WARP_LAUNCH(256);
+    else if (cols == 128) SHG_WARP_LAUNCH(128);
+    else SHG_WARP_LAUNCH(64);
     SHG_LAUNCH_CHECK();
     return 0;
 }

@@ -208,6 +208,154 @@ def two_step(points):
     return np.array(center), height, phi, ratio, kept, outline
 
 
+# ------------------------------------------------- device-assisted limb search
+def gaussian_weights(sigma, truncate=4.0):
+    """scipy.ndimage._gaussian_kernel1d: weights at offsets 0..radius (symmetric)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return phi[radius:]
+
+
+def percentile_from_pair(a, b, n, q):
+    """np.percentile(..., q) (method 'linear') given the two order statistics that
+    bracket it: a = sorted[floor((n-1)q/100)], b = the next one."""
+    virtual = (n - 1) * np.true_divide(q, 100)
+    gamma = virtual - np.floor(virtual)
+    diff = b - a
+    out = a + diff * gamma
+    if gamma >= 0.5:
+        out = b - diff * (1 - gamma)
+    return out
+
+
+def flood_level(counts, edges, fallback):
+    """Threshold of get_flood_image from the 20-bin histogram (reference :176-217)."""
+    c0, c1, c2, c3 = Polynomial.fit(edges[1:], counts, 3).convert().coef
+    disc = 4 * c2 ** 2 - 12 * c3 * c1
+    valley = (-2 * c2 + np.sqrt(disc)) / (6 * c3) if disc >= 0 else fallback
+    start = -1
+    for i in range(len(edges) - 1):
+        if edges[i] <= valley < edges[i + 1]:
+            start = i
+    if start < 0:
+        return fallback
+    i = start
+    while 0 < i < len(edges) - 2:
+        if counts[i - 1] < counts[i]:
+            i -= 1
+        elif counts[i + 1] < counts[i]:
+            i += 1
+        else:
+            break
+    return edges[i - 1] if i >= 1 else edges[i]
+
+
+def _components(flat, cols):
+    """8-connected components of a sorted array of flat pixel indices; labels are
+    numbered 1.. in raster order of each component's first pixel (scipy.ndimage.label)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    n = len(flat)
+    col = flat % cols
+    src, dst = [], []
+    for dr, dc in ((0, 1), (1, -1), (1, 0), (1, 1)):
+        ok = (col + dc >= 0) & (col + dc < cols)
+        target = flat + dr * cols + dc
+        pos = np.searchsorted(flat, target)
+        pos_c = np.minimum(pos, n - 1)
+        hit = ok & (pos < n) & (flat[pos_c] == target)
+        src.append(np.nonzero(hit)[0])
+        dst.append(pos_c[hit])
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    graph = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n))
+    count, lab = connected_components(graph, directed=False)
+    first = np.full(count, n, dtype=np.int64)
+    np.minimum.at(first, lab, np.arange(n))
+    order = np.argsort(first)
+    rank = np.empty(count, dtype=np.int64)
+    rank[order] = np.arange(1, count + 1)
+    return count, rank[lab]
+
+
+def limb_points_device(eng, sums, sigma=2.0):
+    """limb_points() with the image-sized work on the GPU.  `sums` is the int32
+    (rows, cols) device tensor of 4x4 block sums; results are bit-identical to
+    limb_points(sums * 2**-20) because every device step mirrors the operation
+    order of the library call it replaces (csrc/limb.cu)."""
+    rows, cols = sums.shape
+    n = rows * cols
+    scale_img = 2.0 ** -20
+    fallback = 0.9 * (eng.sum_u32(sums) * scale_img) / (rows * cols)
+    bw = int(rows * 0.01)
+    scale = 1.0 / (bw * bw)
+    box = eng.box_sum_u32(sums, bw, bw)
+
+    def blurred(b, s):
+        return (float(b) * scale_img) * s
+
+    prev = int(np.floor((n - 1) * np.true_divide(99, 100)))
+    b_lo, b_hi = eng.select_u32(box, [prev, min(prev + 1, n - 1)])
+    ceiling = percentile_from_pair(blurred(b_lo, scale), blurred(b_hi, scale), n, 99)
+    r_lo, r_hi = eng.blur_range(box, scale, ceiling)
+    first, last = blurred(r_lo, scale), blurred(r_hi, scale)
+    if first == last:
+        first, last = first - 0.5, last + 0.5
+    edges = np.linspace(first, last, 21)
+    counts = eng.blur_hist(box, scale, ceiling, edges)
+    level = flood_level(counts, edges, fallback)
+
+    box5 = eng.box_sum_u32(sums, 5, 5)
+    m_lo, m_hi = eng.select_u32(box5, [(n - 1) // 2, n // 2])
+    s5 = 1.0 / 25
+    median = blurred(m_lo, s5) if n % 2 else np.mean([blurred(m_lo, s5), blurred(m_hi, s5)])
+    low = median / 10
+    high = low * 1.5
+    while True:
+        if sigma <= 0:
+            raise Exception('ERROR: could not find any edges')
+        flat, mag = eng.canny_candidates(box, scale, level, gaussian_weights(sigma), low)
+        if len(flat):
+            count, lab = _components(flat, cols)
+            strong = np.zeros(count + 1, bool)
+            strong[np.unique(lab[mag >= high])] = True
+            keep = strong[lab]
+            flat_e = flat[keep]                                   # canny's edge pixels, raster order
+            if len(flat_e):
+                break
+        sigma -= 0.5
+    n_regions, lab = _components(flat_e, cols)
+    sizes = np.bincount(lab, minlength=n_regions + 1)
+    sizes[0] = -1
+    ranked = sorted(sizes.tolist(), reverse=True)[:min(n_regions, NUM_REG)]
+    chosen = [sizes.tolist().index(s) for s in ranked]
+    sel = np.isin(lab, chosen)
+    pts = np.stack([flat_e[sel] // cols, flat_e[sel] % cols], axis=1)
+    hull = set(map(tuple, pts[ConvexHull(pts).vertices]))
+    kept = np.zeros(len(flat_e), bool)
+    for c in chosen:
+        region = lab == c
+        rp = np.stack([flat_e[region] // cols, flat_e[region] % cols], axis=1)
+        if any(tuple(p) in hull for p in rp):
+            kept |= region
+    lo, hi = pts[:, 0].min(), pts[:, 0].max()
+    span = hi - lo
+    r_all = flat_e // cols
+    band = (r_all >= int(lo + span * EDGE_CROP)) & (r_all < int(hi - span * EDGE_CROP))
+    out = flat_e[kept & band]
+    return (np.stack([out // cols, out % cols], axis=1).astype(float),
+            np.stack([flat_e // cols, flat_e % cols], axis=1))
+
+
+def fit_from_device(eng, sums):
+    """fit_from_block_sums with the limb search on the GPU."""
+    pts, raw = limb_points_device(eng, sums)
+    pts, raw = pts * 4, raw * 4
+    center, height, phi, ratio, kept, outline = two_step(pts)
+    return np.array([center[1], center[0]]), height, phi, ratio, kept, raw, outline
+
+
 def fit_from_block_sums(block_sums):
     """block_sums: (ceil(ih/4), ceil(N/4)) integer sums of 4x4 pixel blocks
     (DN units).  Returns (centre_xy, height, phi, ratio, kept points, raw edge

@@ -46,9 +46,10 @@ def correct_image(image, phi, ratio, center, height, options, print_log=False):
     frames, flip = _as_frames(eng, image)
     n, ih = frames.shape
     mat, mat3, out_shape, _, theta = geometry.warp_plan((ih, n), phi, ratio)
-    lo, hi = eng.minmax(frames)
-    corner = frames[n - 1 if flip else 0, 0:1].cpu().numpy()[0]              # image[0, 0]
-    out = eng.warp(frames, flip, mat3, out_shape, float(corner), lo, hi)
+    with eng.stage('minmax'):
+        mm = eng.minmax_device(frames)
+    with eng.stage('warp'):
+        out = eng.warp_batch(frames, None, flip, mat3, out_shape, mm)[0]
     new_center, new_radius = geometry.moved_circle(np.asarray(center, dtype='d'), height, phi, ratio, (ih, n))
     if print_log:
         basefich0 = options['basefich0']
@@ -73,9 +74,9 @@ def ellipse_to_circle(image, options, basefich):
     Returns (image, (cx, cy, radius), ratio, phi, borders)."""
     eng = get_engine()
     frames, flip = _as_frames(eng, image)
-    with eng.stage('ellipse_fit(host)'):
-        sums = eng.downscale4(frames, flip).cpu().numpy()
-        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_block_sums(sums)
+    with eng.stage('ellipse_fit'):
+        sums = eng.downscale4(frames, flip)
+        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_device(eng, sums)
     src = image if isinstance(image, DeviceImage) else DeviceImage(eng, frames, 'frames', flip)
     fixed, circle, mat3 = correct_image(src, phi, ratio, center, height, options, print_log=True)
     pts = np.ones((kept.shape[0], 3))

@@ -359,37 +359,57 @@ class Engine:
         self.n_launches += 1
         return out
 
+    def minmax_device(self, imgs, sel=None):
+        """Per-image (min, max) of a (S, ...) batch (or one 2-D image), left on the
+        device as an int32 (n, 2) tensor: the warp reads its clip range from it."""
+        if imgs.dim() == 2:
+            imgs = imgs.unsqueeze(0)
+        assert imgs.is_contiguous()
+        n_imgs = imgs.shape[0] if sel is None else len(sel)
+        sel_t = None if sel is None else torch.tensor(list(sel), dtype=torch.int32, device=self.device)
+        mm = self.empty((n_imgs, 2), torch.int32)
+        call('shg_minmax_u16', imgs.data_ptr(), imgs[0].numel(), imgs.stride(0), _ptr(sel_t), n_imgs,
+             mm.data_ptr(), self.stream)
+        self.n_launches += 2
+        return mm
+
     def minmax(self, img):
-        mm = torch.tensor([65535, 0], dtype=torch.int32, device=self.device)
-        call('shg_minmax_u16', img.data_ptr(), img.numel(), mm.data_ptr(), self.stream)
-        self.n_launches += 1
-        lo, hi = mm.cpu().tolist()
+        lo, hi = self.minmax_device(img)[0].cpu().tolist()
         return int(lo), int(hi)
 
-    def minmax_many(self, disk):
-        """(lo, hi) of every image of a (S, N, ih) disk tensor with one device -> host copy."""
-        n = disk.shape[0]
-        mm = torch.tensor([[65535, 0]] * n, dtype=torch.int32, device=self.device)
-        for i in range(n):
-            call('shg_minmax_u16', disk[i].data_ptr(), disk[i].numel(), mm[i].data_ptr(), self.stream)
-        self.n_launches += n
-        return mm.cpu().numpy()
-
     # -------------------------------------------------- circularisation warp
-    def warp(self, disk_s, flip: bool, mat3: np.ndarray, out_shape, cval: float, lo: float, hi: float, out=None):
-        """correct_image's pixel work (ellipse_to_circle.py:112-118) on a
-        frame-major disk; returns the (ih', Wout) uint16 image."""
-        n, ih = disk_s.shape
+    def warp_batch(self, disks, sel, flip: bool, mat3: np.ndarray, out_shape, minmax_dev=None, out=None):
+        """correct_image's pixel work (ellipse_to_circle.py:112-118) on frame-major
+        disks (S, N, ih): images `sel` (None = all) -> (n, rows, cols) uint16, one launch."""
+        if disks.dim() == 2:
+            disks = disks.unsqueeze(0)
+        assert disks.is_contiguous() or disks.stride(1) == disks.shape[2]
+        _, n, ih = disks.shape
         if not (mat3[1, 0] == 0 and mat3[1, 1] == 1 and mat3[1, 2] == 0 and
                 mat3[2, 0] == 0 and mat3[2, 1] == 0 and mat3[2, 2] == 1):
             raise ShgError('warp matrix is not the row-preserving form get_correction_matrix produces')
+        n_imgs = disks.shape[0] if sel is None else len(sel)
+        sel_t = None if sel is None else torch.tensor(list(sel), dtype=torch.int32, device=self.device)
+        if minmax_dev is None:
+            minmax_dev = self.minmax_device(disks, sel)
         oh, ow = int(out_shape[0]), int(out_shape[1])
         if out is None:
-            out = self.empty((oh, ow), torch.uint16)
-        call('shg_warp_rows', disk_s.data_ptr(), n, ih, 1 if flip else 0, float(mat3[0, 0]), float(mat3[0, 1]),
-             float(mat3[0, 2]), float(cval), float(lo), float(hi), out.data_ptr(), oh, ow, self.stream)
+            out = self.empty((n_imgs, oh, ow), torch.uint16)
+        call('shg_warp_rows', disks.data_ptr(), disks.stride(0), _ptr(sel_t), n_imgs, n, ih, 1 if flip else 0,
+             float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), out.data_ptr(),
+             out.stride(0), oh, ow, self.stream)
         self.n_launches += 1
         return out
+
+    def warp(self, disk_s, flip: bool, mat3: np.ndarray, out_shape, cval=None, lo=None, hi=None, out=None):
+        """One image.  cval is image[0][0] and is read on the device; lo / hi
+        default to the image's min / max (what skimage's warp clips to)."""
+        mm = None
+        if lo is not None and hi is not None:
+            mm = torch.tensor([[int(lo), int(hi)]], dtype=torch.int32, device=self.device)
+        res = self.warp_batch(disk_s, None, flip, mat3, out_shape, mm,
+                              None if out is None else out.unsqueeze(0))
+        return res[0]
 
     def downscale4(self, disk_s, flip: bool):
         """4x4 block sums of the (ih, N) image (ellipse_to_circle.py:301)."""
@@ -399,6 +419,77 @@ class Engine:
              out.shape[1], self.stream)
         self.n_launches += 1
         return out
+
+    # ------------------------------------------- limb detection (ellipse fit)
+    def box_sum_u32(self, img, kw: int, kh: int):
+        rows, cols = img.shape
+        out = self.empty((rows, cols), torch.int32)
+        tmp = self.empty((rows, cols), torch.int32)
+        call('shg_box_sum_u32', img.data_ptr(), rows, cols, int(kw), int(kh), out.data_ptr(), tmp.data_ptr(),
+             self.stream)
+        self.n_launches += 2
+        return out
+
+    def sum_u32(self, img) -> int:
+        out = self.empty((1,), torch.int64)
+        call('shg_sum_u32', img.data_ptr(), img.numel(), out.data_ptr(), self.stream)
+        self.n_launches += 1
+        return int(out.cpu().item())
+
+    def select_u32(self, vals, ranks):
+        """Exact order statistics (0-based ranks) of a uint32 device array."""
+        ranks = [int(r) for r in ranks]
+        r = (C.c_int64 * len(ranks))(*ranks)
+        out = (C.c_uint32 * len(ranks))()
+        work = self.empty((256,), torch.int32)
+        call('shg_select_u32', vals.data_ptr(), vals.numel(), r, len(ranks), out, work.data_ptr(), self.stream)
+        self.n_launches += 4 * len(ranks)
+        return [int(v) for v in out]
+
+    def blur_range(self, box, scale: float, ceiling: float):
+        out = self.empty((2,), torch.int32)
+        call('shg_blur_range', box.data_ptr(), box.numel(), float(scale), float(ceiling), out.data_ptr(), self.stream)
+        self.n_launches += 1
+        lo, hi = out.cpu().numpy().view(np.uint32).tolist()
+        return int(lo), int(hi)
+
+    def blur_hist(self, box, scale: float, ceiling: float, edges: np.ndarray):
+        edges = np.ascontiguousarray(edges, dtype=np.float64)
+        n_bins = len(edges) - 1
+        counts = self.empty((32,), torch.int64)
+        call('shg_blur_hist', box.data_ptr(), box.numel(), float(scale), float(ceiling),
+             edges.ctypes.data_as(C.POINTER(C.c_double)), n_bins, counts.data_ptr(), self.stream)
+        self.n_launches += 1
+        return counts.cpu().numpy()[:n_bins]
+
+    def canny_candidates(self, box, scale: float, level: float, weights: np.ndarray, low: float):
+        """Thin-edge pixels of canny(flood image): (flat indices sorted ascending, magnitudes)."""
+        rows, cols = box.shape
+        n = rows * cols
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        buf = self.empty((6, n), torch.float64)          # smoothed, tmp0, tmp1, gi, gj, mag
+        call('shg_flood_smooth', box.data_ptr(), rows, cols, float(scale), float(level),
+             w.ctypes.data_as(C.POINTER(C.c_double)), len(w) - 1, float(np.finfo(np.float64).eps),
+             buf[0].data_ptr(), buf[1].data_ptr(), self.stream)
+        call('shg_sobel_mag', buf[0].data_ptr(), rows, cols, buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(),
+             self.stream)
+        self.n_launches += 6
+        cap = 1 << 20
+        while True:
+            count = self.empty((1,), torch.int32)
+            idx = self.empty((cap,), torch.int32)
+            mag = self.empty((cap,), torch.float64)
+            call('shg_nms_candidates', buf[3].data_ptr(), buf[4].data_ptr(), buf[5].data_ptr(), rows, cols,
+                 float(low), count.data_ptr(), cap, idx.data_ptr(), mag.data_ptr(), self.stream)
+            self.n_launches += 1
+            m = int(count.cpu().item())
+            if m <= cap:
+                break
+            cap = m
+        idx_h = idx[:m].cpu().numpy().view(np.uint32).astype(np.int64)
+        mag_h = mag[:m].cpu().numpy()
+        order = np.argsort(idx_h, kind='stable')
+        return idx_h[order], mag_h[order]
 
     # ------------------------------------------------------- transversalium
     @property
@@ -422,56 +513,52 @@ class Engine:
             xb.append(math.floor(min(cx + dx, borders[2])))
         return y1, y2, np.asarray(rows, np.int32), np.asarray(xa, np.int32), np.asarray(xb, np.int32)
 
-    def transversalium_row_stats(self, img, rows, xa, xb):
-        """Per-row robust mean of log(img[y]/img[y-1]) over [xa, xb) (solex_util.py:392-395)."""
+    def transversalium_row_stats(self, imgs, rows, xa, xb):
+        """Per-row robust mean of log(img[y]/img[y-1]) over [xa, xb) (solex_util.py:392-395)
+        for one (h, w) image -> (n,), or a (S, h, w) batch sharing the chords -> (S, n).
+        One launch, one device -> host copy."""
+        single = imgs.dim() == 2
+        if single:
+            imgs = imgs.unsqueeze(0)
         n = len(rows)
         if n == 0:
-            return np.zeros(0)
-        h, w = img.shape
+            return np.zeros(0) if single else np.zeros((imgs.shape[0], 0))
+        n_imgs, h, w = imgs.shape
+        assert imgs.stride(1) == w and imgs.stride(2) == 1
         if rows.min() < 1 or rows.max() >= h or xa.min() < 0 or xb.max() > w:
             raise IndexError('transversalium chord outside the image')     # the reference would raise / wrap too
-        idx = torch.from_numpy(np.stack([rows, xa, xb])).to(self.device)
-        out = self.empty((n,), torch.float64)
+        idx = torch.from_numpy(np.stack([rows, xa, xb]).astype(np.int32)).to(self.device)
+        out = self.empty((n_imgs, n), torch.float64)
         max_len = int(max(0, (xb - xa).max()))
-        wb = int(lib.shg_transv_workspace_bytes(n, max_len))
+        wb = int(lib.shg_transv_workspace_bytes(n, max_len, n_imgs))
         work = self.empty((wb,), torch.uint8) if wb > 0 else None
-        call('shg_transv_row_stats', img.data_ptr(), h, w, idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(),
-             n, max_len, self.logtab.data_ptr(), out.data_ptr(), _ptr(work), wb, self.stream)
+        call('shg_transv_row_stats', imgs.data_ptr(), h, w, n_imgs, imgs.stride(0), idx[0].data_ptr(),
+             idx[1].data_ptr(), idx[2].data_ptr(), n, max_len, self.logtab.data_ptr(), out.data_ptr(),
+             _ptr(work), wb, self.stream)
         self.n_launches += 1
-        return out.cpu().numpy()
+        res = out.cpu().numpy()
+        return res[0] if single else res
 
-    def transversalium_row_stats_many(self, imgs, rows, xa, xb):
-        """Same chords on several images (every shift of one scan shares the
-        circle): one launch per image, one device -> host copy.  Returns (S, n)."""
-        n = len(rows)
-        if n == 0 or len(imgs) == 0:
-            return np.zeros((len(imgs), 0))
-        h, w = imgs[0].shape
-        if rows.min() < 1 or rows.max() >= h or xa.min() < 0 or xb.max() > w:
-            raise IndexError('transversalium chord outside the image')
-        idx = torch.from_numpy(np.stack([rows, xa, xb])).to(self.device)
-        out = self.empty((len(imgs), n), torch.float64)
-        max_len = int(max(0, (xb - xa).max()))
-        wb = int(lib.shg_transv_workspace_bytes(n, max_len))
-        work = self.empty((wb,), torch.uint8) if wb > 0 else None
-        tab = self.logtab.data_ptr()
-        for i, img in enumerate(imgs):
-            assert tuple(img.shape) == (h, w)
-            call('shg_transv_row_stats', img.data_ptr(), h, w, idx[0].data_ptr(), idx[1].data_ptr(),
-                 idx[2].data_ptr(), n, max_len, tab, out[i].data_ptr(), _ptr(work), wb, self.stream)
-        self.n_launches += len(imgs)
-        return out.cpu().numpy()
-
-    def row_scale(self, img, gain: np.ndarray, out=None):
-        """(img.T * c).T, clip 65535, truncate (solex_util.py:489,515-516)."""
-        h, w = img.shape
+    def row_scale(self, imgs, gain, out=None):
+        """(img.T * c).T, clip 65535, truncate (solex_util.py:489,515-516) for one
+        image with gain (h,), or a (S, h, w) batch with gains (S, h)."""
+        single = imgs.dim() == 2
+        if single:
+            imgs = imgs.unsqueeze(0)
+        n_imgs, h, w = imgs.shape
+        assert imgs.stride(1) == w and imgs.stride(2) == 1
         g = gain if isinstance(gain, torch.Tensor) else \
             torch.from_numpy(np.ascontiguousarray(gain, dtype=np.float64)).to(self.device)
+        assert g.numel() == n_imgs * h
         if out is None:
-            out = self.empty((h, w), torch.uint16)
-        call('shg_row_scale_u16', img.data_ptr(), h, w, g.data_ptr(), out.data_ptr(), self.stream)
+            out = self.empty((n_imgs, h, w), torch.uint16)
+        elif out.dim() == 2:
+            out = out.unsqueeze(0)
+        assert out.stride(0) == imgs.stride(0) or n_imgs == 1
+        call('shg_row_scale_u16', imgs.data_ptr(), h, w, n_imgs, imgs.stride(0), g.data_ptr(), out.data_ptr(),
+             self.stream)
         self.n_launches += 1
-        return out
+        return out[0] if single else out
 
 
 _engines = {}

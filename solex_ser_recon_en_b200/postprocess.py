@@ -27,8 +27,26 @@ def frames_of(eng, image):
     return torch.from_numpy(dn).to(eng.device), False
 
 
+def _common_base(pairs):
+    """If every image is a slice of one (S, N, ih) disk tensor with the same flip,
+    return (base tensor view, indices); else None."""
+    first = pairs[0][0]
+    flip = pairs[0][1]
+    stride = first.shape[0] * first.shape[1]
+    base_ptr = min(p[0].data_ptr() for p in pairs)
+    idx = []
+    for fr, fl in pairs:
+        off = (fr.data_ptr() - base_ptr) // 2
+        if fl != flip or fr.shape != first.shape or not fr.is_contiguous() or off % stride:
+            return None
+        idx.append(off // stride)
+    return base_ptr, idx, stride
+
+
 def circularise_many(images, phi, ratio):
-    """Warp every image with the same (phi, ratio).  Returns
+    """Warp every image with the same (phi, ratio): one min/max launch and one
+    warp launch for the whole set when the images are slices of one disk tensor
+    (the normal case: read_video_improved's output).  Returns
     (list of row-major DeviceImage, mat 2x2, mat3, theta)."""
     eng = get_engine()
     if not images:
@@ -36,40 +54,56 @@ def circularise_many(images, phi, ratio):
     pairs = [frames_of(eng, im) for im in images]
     n, ih = pairs[0][0].shape
     mat, mat3, out_shape, _, theta = geometry.warp_plan((ih, n), phi, ratio)
-    with eng.stage('minmax'):
-        mm = torch.tensor([[65535, 0]] * len(pairs), dtype=torch.int32, device=eng.device)
-        corners = eng.empty((len(pairs),), torch.uint16)
-        from ._lib import call
-        for i, (fr, flip) in enumerate(pairs):
-            call('shg_minmax_u16', fr.data_ptr(), fr.numel(), mm[i].data_ptr(), eng.stream)
-            corners[i:i + 1].copy_(fr[n - 1 if flip else 0, 0:1])                # image[0, 0]
-        eng.n_launches += len(pairs)
-        mm_h = mm.cpu().numpy()
-        corners_h = corners.cpu().numpy()
-    out = []
-    with eng.stage('warp'):
-        for i, (fr, flip) in enumerate(pairs):
-            t = eng.warp(fr, flip, mat3, out_shape, float(corners_h[i]), float(mm_h[i, 0]), float(mm_h[i, 1]))
-            out.append(DeviceImage(eng, t))
-    return out, mat, mat3, theta
+    common = _common_base(pairs)
+    if common is not None and len(pairs) > 1:
+        base_ptr, idx, stride = common
+        first = min(pairs, key=lambda p: p[0].data_ptr())[0]
+        span = max(idx) + 1
+        # a (span, N, ih) view over the shared storage that starts at the lowest slice
+        base = torch.as_strided(first, (span, n, ih), (stride, ih, 1))
+        with eng.stage('minmax'):
+            mm = eng.minmax_device(base, idx)
+        with eng.stage('warp'):
+            out = eng.warp_batch(base, idx, pairs[0][1], mat3, out_shape, mm)
+        return [DeviceImage(eng, out[i]) for i in range(len(pairs))], mat, mat3, theta
+    res = []
+    for fr, flip in pairs:
+        with eng.stage('minmax'):
+            mm = eng.minmax_device(fr)
+        with eng.stage('warp'):
+            res.append(DeviceImage(eng, eng.warp_batch(fr, None, flip, mat3, out_shape, mm)[0]))
+    return res, mat, mat3, theta
+
+
+def _stack_rows(eng, images):
+    """(S, h, w) tensor of row-major device images (a view when they already are
+    consecutive slices of one tensor, else a copy)."""
+    tens = [im.rows_tensor() if isinstance(im, DeviceImage) else
+            torch.from_numpy(np.ascontiguousarray(np.asarray(im), dtype=np.uint16)).to(eng.device) for im in images]
+    h, w = tens[0].shape
+    step = h * w * 2
+    if all(t.is_contiguous() and t.shape == (h, w) and t.data_ptr() == tens[0].data_ptr() + i * step
+           for i, t in enumerate(tens)) and tens[0].untyped_storage().nbytes() - \
+            (tens[0].data_ptr() - tens[0].untyped_storage().data_ptr()) >= len(tens) * step:
+        return torch.as_strided(tens[0], (len(tens), h, w), (h * w, w, 1))
+    return torch.stack(tens)
 
 
 def detransversalium_many(images, circle, borders, strength):
     """Transversalium correction of several row-major device images that share
     the disk geometry.  Returns (list of DeviceImage, gains (S, rows))."""
-    from .solex_util import transversalium_gain
+    from .solex_util import transversalium_gains
     eng = get_engine()
     if not images:
         return [], np.zeros((0, 0))
-    tens = [im.rows_tensor() if isinstance(im, DeviceImage) else
-            torch.from_numpy(np.ascontiguousarray(np.asarray(im), dtype=np.uint16)).to(eng.device) for im in images]
+    batch = _stack_rows(eng, images)
     y1, y2, rows, xa, xb = eng.transversalium_chords(circle, borders)
     with eng.stage('transv_stats'):
-        stats = eng.transversalium_row_stats_many(tens, rows, xa, xb)
-    h = tens[0].shape[0]
+        stats = eng.transversalium_row_stats(batch, rows, xa, xb)
+    h = batch.shape[1]
     with eng.stage('transv_gain_host'):
-        gains = np.stack([transversalium_gain(np.concatenate([[0.0], s]), y1, y2, h, strength) for s in stats])
+        gains = transversalium_gains(stats, y1, y2, h, strength)
         gains_d = torch.from_numpy(gains).to(eng.device)
     with eng.stage('row_scale'):
-        out = [DeviceImage(eng, eng.row_scale(t, gains_d[i])) for i, t in enumerate(tens)]
-    return out, gains
+        out = eng.row_scale(batch, gains_d)
+    return [DeviceImage(eng, out[i]) for i in range(len(images))], gains

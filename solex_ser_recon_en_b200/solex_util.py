@@ -293,6 +293,59 @@ def transversalium_gain(y_ratios_r, y1, y2, n_rows, strength):
     return c
 
 
+def savgol_cubic_rows(x, window):
+    """scipy.signal.savgol_filter(x, window, 3, axis=-1) (mode 'interp') for a
+    (S, n) batch in O(S*n): the smoothing weights of a local cubic fit are
+    a + b*k^2 in the offset k, so the filter is a combination of windowed sums of
+    x, j*x and j^2*x taken from prefix sums; the first / last window//2 samples
+    come from a cubic fitted to the first / last window, as scipy does.  Agrees
+    with scipy to ~1e-12 of the signal scale (the gain tolerance is 1e-5)."""
+    x = np.asarray(x, dtype=np.float64)
+    s, n = x.shape
+    m = window // 2
+    if window < 5 or window > n:
+        return savgol_filter(x, window, 3, axis=-1)
+    den = (2 * m + 3) * (2 * m + 1) * (2 * m - 1)
+    a = 3.0 * (3 * m * m + 3 * m - 1) / den
+    b = -15.0 / den
+    j = np.arange(n, dtype=np.float64) - n / 2.0
+    p0 = np.concatenate([np.zeros((s, 1)), np.cumsum(x, axis=1)], axis=1)
+    p1 = np.concatenate([np.zeros((s, 1)), np.cumsum(x * j, axis=1)], axis=1)
+    p2 = np.concatenate([np.zeros((s, 1)), np.cumsum(x * j * j, axis=1)], axis=1)
+    k = n - window + 1                                                    # interior outputs i = m .. n-m-1
+    s0 = p0[:, window:window + k] - p0[:, :k]
+    s1 = p1[:, window:window + k] - p1[:, :k]
+    s2 = p2[:, window:window + k] - p2[:, :k]
+    ji = j[m:n - m]
+    out = np.empty_like(x)
+    out[:, m:n - m] = a * s0 + b * (s2 - 2.0 * ji * s1 + ji * ji * s0)
+    t = np.arange(window, dtype=np.float64)
+    head = np.polyfit(t, x[:, :window].T, 3)                              # (4, S), highest power first
+    tail = np.polyfit(t, x[:, n - window:].T, 3)
+    th = np.arange(0, m, dtype=np.float64)[:, None]
+    tt = np.arange(window - m, window, dtype=np.float64)[:, None]
+    out[:, :m] = (((head[0] * th + head[1]) * th + head[2]) * th + head[3]).T
+    out[:, n - m:] = (((tail[0] * tt + tail[1]) * tt + tail[2]) * tt + tail[3]).T
+    return out
+
+
+def transversalium_gains(stats, y1, y2, n_rows, strength):
+    """transversalium_gain for a (S, n) batch of per-row statistics in one
+    vectorised pass (savgol_filter, cumsum and exp work along the last axis)."""
+    stats = np.asarray(stats, dtype=np.float64)
+    s = stats.shape[0]
+    ratios = np.concatenate([np.zeros((s, 1)), stats], axis=1)           # y_ratios_r[0] = 0 (solex_util.py:386)
+    n = ratios.shape[1]
+    trend = savgol_cubic_rows(ratios, min(strength, n // 2 * 2 - 1))
+    detrended = ratios - trend
+    detrended -= np.mean(detrended, axis=1, keepdims=True)
+    correction = np.exp(-np.cumsum(detrended, axis=1))
+    tapered = np.ones(n) + (correction - np.ones(n)) * tukey_taper(n)
+    c = np.ones((s, n_rows))
+    c[:, y1:y2] = tapered
+    return c
+
+
 def correct_transversalium2(img, circle, borders, options, reqFlag, basefich):
     """Remove horizontal line defects: per-row gain from robust row-to-row
     log-ratios inside the disk.  `img` may be a DeviceImage or an ndarray;

@@ -424,3 +424,62 @@ def test_synth_is_range_consistent(eng):
     a = eng.synth_stack(geom, k0=0, n=40, seed=3).host_frames(0, 40)
     b = eng.synth_stack(geom, k0=40, n=50, seed=3).host_frames(0, 50)
     assert np.array_equal(np.concatenate([a, b]), whole)
+
+
+# ------------------------------------------------------ limb detection (a11)
+def _disk_image(rng, rows, cols, ry, rx, noise=12.0, tilt=0.0):
+    r = (np.arange(rows)[:, None] - rows / 2) / ry
+    c = (np.arange(cols)[None, :] - cols / 2 - tilt * (np.arange(rows)[:, None] - rows / 2)) / rx
+    rho2 = r * r + c * c
+    img = np.where(rho2 < 1, np.sqrt(np.maximum(1 - 0.6 * rho2, 0)), 0.02) * 8000 + 300 + rng.normal(0, noise, rho2.shape)
+    return np.clip(np.rint(img), 0, 65535).astype(np.uint16)
+
+
+@pytest.mark.parametrize('shape,ry,rx,tilt', [((512, 900), 200, 380, 0.0), ((640, 333), 250, 120, 0.1),
+                                               ((1023, 2047), 400, 850, -0.05)])
+def test_limb_points_device_equals_host_pipeline(eng, shape, ry, rx, tilt):
+    """The GPU limb search must give the SAME edge pixels as the host NumPy /
+    SciPy / OpenCV pipeline (which the golden tests pin to the reference)."""
+    import torch
+    from solex_ser_recon_en_b200 import ellipse_fit as E
+    rng = np.random.default_rng(shape[0])
+    img = _disk_image(rng, shape[0], shape[1], ry, rx, tilt=tilt)
+    fm = torch.from_numpy(np.ascontiguousarray(img.T)).to(eng.device)          # frame-major
+    sums = eng.downscale4(fm, False)
+    sums_h = sums.cpu().numpy()
+    want_pts, want_raw = E.limb_points(sums_h.astype(np.float64) * 2.0 ** -20)
+    got_pts, got_raw = E.limb_points_device(eng, sums)
+    assert np.array_equal(got_raw, want_raw)
+    assert np.array_equal(got_pts, want_pts)
+    a = E.fit_from_block_sums(sums_h)
+    b = E.fit_from_device(eng, sums)
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
+def test_limb_building_blocks(eng):
+    """box sums == cv2.blur numerators, order statistics == np.partition, histogram == np.histogram."""
+    import cv2
+    import torch
+    rng = np.random.default_rng(8)
+    s = rng.integers(0, 16 * 65535, size=(300, 417)).astype(np.uint32)
+    d = torch.from_numpy(s.view(np.int32)).to(eng.device)
+    for kw, kh in ((3, 3), (5, 5), (10, 10), (7, 4)):
+        box = eng.box_sum_u32(d, kw, kh).cpu().numpy().view(np.uint32)
+        img = s.astype(np.float64) * 2.0 ** -20
+        want = cv2.blur(img, ksize=(kw, kh))
+        got = (box.astype(np.float64) * 2.0 ** -20) * (1.0 / (kw * kh))
+        assert np.array_equal(got, want), (kw, kh)
+    assert eng.sum_u32(d) == int(s.astype(np.uint64).sum())
+    flat = np.sort(s.ravel())
+    ranks = [0, 1, 777, flat.size // 2, flat.size - 1]
+    assert eng.select_u32(d, ranks) == [int(flat[r]) for r in ranks]
+    box = eng.box_sum_u32(d, 5, 5)
+    scale = 1.0 / 25
+    blurred = (box.cpu().numpy().view(np.uint32).astype(np.float64) * 2.0 ** -20) * scale
+    ceiling = np.percentile(blurred, 99)
+    data = blurred[blurred < ceiling]
+    counts, edges = np.histogram(data, bins=20)
+    lo, hi = eng.blur_range(box, scale, ceiling)
+    assert ((lo * 2.0 ** -20) * scale, (hi * 2.0 ** -20) * scale) == (data.min(), data.max())
+    assert np.array_equal(eng.blur_hist(box, scale, ceiling, edges), counts)
