@@ -54,6 +54,7 @@ _PROTOS = {
     'shg_log_table': (i32, [vp, vp]),
     'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),
     'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]),
+    'shg_transv_gain': (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]),
     'shg_row_scale_u16': (i32, [vp, i32, i32, i32, i64, vp, vp, vp]),
     'shg_ingest_create': (i32, [i32, i64, i32, i32, C.POINTER(vp)]),
     'shg_ingest_destroy': (i32, [vp]),

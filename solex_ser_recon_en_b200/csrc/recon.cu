@@ -16,6 +16,8 @@
 // Bound: HBM.  Algorithmic bytes / frame = ih*nb*bytes_per_px + n_shifts*ih*2.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -114,8 +116,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-template <typename T, int TX, int STAGES>
-__global__ void __launch_bounds__(TX)
+// TX columns x G shift groups per CTA: thread (col, grp) walks a contiguous
+// slice of each run of shifts for its column, so consecutive shifts reuse the
+// previous right tap as their left tap (one shared-memory load + one
+// conversion per output instead of two).
+template <typename T, int TX, int STAGES, int G>
+__global__ void __launch_bounds__(TX * G)
 recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ShiftTable tab,
                  int64_t n_frames, int W, int H, int n_tx, int stage_elems,
                  const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
@@ -127,6 +133,7 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
     __shared__ __align__(8) uint64_t full[STAGES];
 
     const int tid = threadIdx.x;
+    const int col = tid % TX, grp = tid / TX;
     const int64_t n_tiles = n_frames * n_tx;
     const int64_t first = blockIdx.x, stride = gridDim.x;
     const uint32_t stage_bytes = (uint32_t)stage_elems * sizeof(T);
@@ -160,7 +167,7 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
         const uint32_t phase = (it / STAGES) & 1;
         const int tx = (int)(tile % n_tx);
         const int64_t k = tile / n_tx;
-        const int x = tx * TX + tid;
+        const int x = tx * TX + col;
         const bool live = x < W;
         const int i = W - 1 - x;
         int f = 0;
@@ -170,17 +177,23 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
         mbar_wait(&full[stage], phase);
 
         if (live) {
-            const T* buf = stage_buf + (size_t)stage * stage_elems + tid;
+            const T* buf = stage_buf + (size_t)stage * stage_elems + col;
             uint16_t* out = disk + (k0_out + k) * W + i;
             for (int r = 0; r < tab.n_runs; ++r) {
                 const T* rb = buf + tab.run_off[r];
                 const int base = row0[tx * tab.n_runs + r];
-                const int j1 = tab.run_first[r + 1];
-                for (int j = tab.run_first[r]; j < j1; ++j) {
+                const int ja = tab.run_first[r], jb = tab.run_first[r + 1];
+                const int per = (jb - ja + G - 1) / G;
+                const int j0 = ja + grp * per, j1 = min(jb, j0 + per);
+                int prev = -0x40000000;
+                double R = 0.0;
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j) {
                     const int il = min(max(f + tab.sh[j], 0), iw - 2) - base;
-                    const T a = rb[il * TX];
-                    const T b = rb[(il + 1) * TX];
-                    out[tab.slot[j] * shift_stride] = lerp_trunc(px_to_double<T>(a), px_to_double<T>(b), wl, wr);
+                    const double L = (il == prev + 1) ? R : px_to_double<T>(rb[il * TX]);
+                    R = px_to_double<T>(rb[(il + 1) * TX]);
+                    prev = il;
+                    out[tab.slot[j] * shift_stride] = lerp_trunc(L, R, wl, wr);
                 }
             }
         }
@@ -290,10 +303,18 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     const int64_t row_bytes = (int64_t)W * bytes_per_px;
     bool tma = rot && impl != 1 && row_bytes % 16 == 0 && ((int64_t)H * row_bytes) % 16 == 0 &&
                ((uintptr_t)d_frames % 16 == 0) && n_frames < (1LL << 31);
-    int TX = 0, stages = 0;
+    int TX = 0, stages = 0, G = 4;
     if (tma) {
-        // tile width: as wide as shared memory allows with >= 3 stages
-        for (int cand : {256, 128, 64}) {
+        // tile width / shift groups: TX*G threads per CTA.  Default 128 columns x 4 groups
+        // (two CTAs per SM with 4 stages at config-5 band heights); SHG_RECON_TX / _G override for tuning.
+        int want_tx = 128;
+        if (const char* e = getenv("SHG_RECON_TX")) want_tx = atoi(e);
+        if (const char* e = getenv("SHG_RECON_G")) G = atoi(e);
+        if (G != 1 && G != 2 && G != 4 && G != 8) G = 4;
+        int cands[3] = {want_tx, 128, 64};
+        for (int cand : cands) {
+            if (cand != 64 && cand != 128 && cand != 256) continue;
+            if (cand * G > 1024) continue;
             if (cand > 64 && cand / 2 >= W) continue;
             const int n_tx = (W + cand - 1) / cand;
             plan.row0.assign((size_t)n_tx * plan.tab.n_runs, 0);
@@ -323,7 +344,8 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
             const int max_stages = (int)(200 * 1024 / sbytes);
             if (max_stages >= 3) {
                 TX = cand; plan.n_tx = n_tx; plan.stage_elems = elems;
-                stages = std::min(max_stages, 4);
+                // prefer two CTAs per SM when four stages of this tile fit in half the shared memory
+                stages = (4 * sbytes + 2048 <= 110 * 1024) ? 4 : std::min(max_stages, 4);
                 break;
             }
         }
@@ -380,20 +402,29 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     SHG_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = (size_t)plan.stage_elems * bytes_per_px * stages + 128;
     const int64_t n_tiles = n_frames * plan.n_tx;
-    const int ctas_per_sm = std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const int by_smem = std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const int by_threads = std::max(1, 2048 / (TX * G));
+    const int ctas_per_sm = std::min(by_smem, by_threads);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * ctas_per_sm);
 
-#define SHG_LAUNCH_TMA(T, TXV, ST)                                                                         \
+#define SHG_LAUNCH_TMA(T, TXV, ST, GV)                                                                     \
     do {                                                                                                   \
-        auto kern = recon_tma_kernel<T, TXV, ST>;                                                          \
+        auto kern = recon_tma_kernel<T, TXV, ST, GV>;                                                      \
         SHG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        kern<<<grid, TXV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, d_fl,    \
-                                      d_lw, d_rw, d_row0, d_disk, shift_stride, k0_out);                   \
+        kern<<<grid, TXV * GV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, d_fl, \
+                                           d_lw, d_rw, d_row0, d_disk, shift_stride, k0_out);              \
+    } while (0)
+#define SHG_DISPATCH_G(T, TXV, ST)                                           \
+    do {                                                                     \
+        if (G == 1) SHG_LAUNCH_TMA(T, TXV, ST, 1);                           \
+        else if (G == 2) SHG_LAUNCH_TMA(T, TXV, ST, 2);                      \
+        else if (G == 8 && TXV <= 128) SHG_LAUNCH_TMA(T, TXV, ST, (TXV <= 128 ? 8 : 4)); \
+        else SHG_LAUNCH_TMA(T, TXV, ST, 4);                                  \
     } while (0)
 #define SHG_DISPATCH_ST(T, TXV)                                  \
     do {                                                         \
-        if (stages >= 4) SHG_LAUNCH_TMA(T, TXV, 4);              \
-        else SHG_LAUNCH_TMA(T, TXV, 3);                          \
+        if (stages >= 4) SHG_DISPATCH_G(T, TXV, 4);              \
+        else SHG_DISPATCH_G(T, TXV, 3);                          \
     } while (0)
 #define SHG_DISPATCH_TX(T)                                       \
     do {                                                         \

@@ -342,6 +342,133 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     if (threadIdx.x == 0) out[slot] = sum / cnt;
 }
 
+// Per-row gain from the per-row statistics (reference solex_util.py:400-404, 456-479):
+//   trend = savgol_filter(ratios, window, 3)  (mode 'interp': cubic fitted to the first / last window at the ends)
+//   detrended = ratios - trend; detrended -= mean; correction = exp(-cumsum(detrended))
+//   gain[y1:y2] = 1 + (correction - 1) * taper, 1 elsewhere.
+// One CTA per image; ratios / detrended live in shared memory.
+constexpr int kGT = 256;
+
+__device__ void cubic_fit_window(const double* x, int w, double* sol /* smem[4]: coefficients in u */, double* red) {
+    // least squares cubic in u = (t - c)/c, c = (w-1)/2, by moment sums + 4x4 elimination
+    const double c = 0.5 * (w - 1);
+    double mom[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) mom[j] = 0.0;
+    for (int t = threadIdx.x; t < w; t += kGT) {
+        const double u = ((double)t - c) / c;
+        double p = 1.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            mom[k] += p;
+            if (k < 4) mom[7 + k] += p * x[t];
+            p *= u;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) mom[j] = warp_sum(mom[j]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int j = 0; j < 11; ++j) red[j * 8 + warp] = mom[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double M[11];
+        for (int j = 0; j < 11; ++j) {
+            double t = 0.0;
+            for (int q = 0; q < kGT / 32; ++q) t += red[j * 8 + q];
+            M[j] = t;
+        }
+        double A[4][5];
+        for (int r = 0; r < 4; ++r) {
+            for (int q = 0; q < 4; ++q) A[r][q] = M[r + q];
+            A[r][4] = M[7 + r];
+        }
+        for (int q = 0; q < 4; ++q) {
+            int piv = q;
+            for (int r = q + 1; r < 4; ++r)
+                if (fabs(A[r][q]) > fabs(A[piv][q])) piv = r;
+            for (int k = 0; k < 5; ++k) { const double t = A[q][k]; A[q][k] = A[piv][k]; A[piv][k] = t; }
+            for (int r = q + 1; r < 4; ++r) {
+                const double f = A[r][q] / A[q][q];
+                for (int k = q; k < 5; ++k) A[r][k] -= f * A[q][k];
+            }
+        }
+        for (int r = 3; r >= 0; --r) {
+            double t = A[r][4];
+            for (int k = r + 1; k < 4; ++k) t -= A[r][k] * sol[k];
+            sol[r] = t / A[r][r];
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGT)
+transv_gain_kernel(const double* __restrict__ stats /* [n_imgs][n-1] */, int n, int window,
+                   const double* __restrict__ coeffs /* [window] */, const double* __restrict__ taper /* [n] */,
+                   int y1, int n_rows, double* __restrict__ gains /* [n_imgs][n_rows] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* r = reinterpret_cast<double*>(smem_raw);          // ratios, then cumsum
+    double* d = r + n;                                          // detrended
+    double* red = d + n;                                        // 11*8 scratch
+    double* sol = red + 96;
+    const int img = blockIdx.x;
+    const double* st = stats + (int64_t)img * (n - 1);
+    double* g = gains + (int64_t)img * n_rows;
+    for (int i = threadIdx.x; i < n; i += kGT) r[i] = i == 0 ? 0.0 : st[i - 1];
+    for (int i = threadIdx.x; i < n_rows; i += kGT)
+        if (i < y1 || i >= y1 + n) g[i] = 1.0;
+    __syncthreads();
+    const int m = window / 2;
+    // interior of the filter
+    for (int i = m + threadIdx.x; i < n - m; i += kGT) {
+        double acc = 0.0;
+        const double* x = r + (i - m);
+        for (int k = 0; k < window; ++k) acc += coeffs[window - 1 - k] * x[k];
+        d[i] = r[i] - acc;
+    }
+    // ends: cubic through the first / last window
+    const double c = 0.5 * (window - 1);
+    cubic_fit_window(r, window, sol, red);
+    for (int i = threadIdx.x; i < m; i += kGT) {
+        const double u = ((double)i - c) / c;
+        d[i] = r[i] - (((sol[3] * u + sol[2]) * u + sol[1]) * u + sol[0]);
+    }
+    __syncthreads();
+    cubic_fit_window(r + (n - window), window, sol, red);
+    for (int i = threadIdx.x; i < m; i += kGT) {
+        const int t = window - m + i;
+        const double u = ((double)t - c) / c;
+        d[n - m + i] = r[n - m + i] - (((sol[3] * u + sol[2]) * u + sol[1]) * u + sol[0]);
+    }
+    __syncthreads();
+    // mean
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += kGT) s += d[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double mean = 0.0;
+    for (int q = 0; q < kGT / 32; ++q) mean += red[q];
+    mean /= n;
+    __syncthreads();
+    // cumsum: contiguous chunk per thread, then offsets
+    const int per = (n + kGT - 1) / kGT;
+    const int a = min(n, (int)threadIdx.x * per), b = min(n, a + per);
+    double run = 0.0;
+    for (int i = a; i < b; ++i) { run += d[i] - mean; r[i] = run; }
+    __syncthreads();
+    d[threadIdx.x] = run;                                       // chunk totals (d[] is no longer needed; n >= kGT)
+    __syncthreads();
+    double off = 0.0;
+    for (int q = 0; q < (int)threadIdx.x; ++q) off += d[q];
+    for (int i = a; i < b; ++i) {
+        const double corr = exp(-(r[i] + off));
+        g[y1 + i] = 1.0 + (corr - 1.0) * taper[i];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 log_table_kernel(double* __restrict__ tab) {
     const int v = blockIdx.x * 256 + threadIdx.x;
@@ -452,6 +579,24 @@ extern "C" int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, int 
     const int per_row = std::max(1, std::min(8, (cols / 8 + 255) / 256));
     row_scale_kernel<<<dim3(per_row, rows, n_imgs), 256, 0, as_stream(stream)>>>(d_img, img_stride, rows, cols, d_gain,
                                                                                 d_out);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shg_transv_gain(const double* d_stats, int n_imgs, int n, int window, const double* d_coeffs,
+                               const double* d_taper, int y1, int n_rows, double* d_gains, void* stream) {
+    if (n_imgs <= 0) return 0;
+    SHG_REQUIRE(window >= 5 && (window & 1) && window <= n, "shg_transv_gain: window %d for %d rows", window, n);
+    SHG_REQUIRE(y1 >= 0 && y1 + n <= n_rows && n >= kGT / 32, "shg_transv_gain: rows [%d, %d) outside the image", y1, y1 + n);
+    SHG_REQUIRE(n >= kGT, "shg_transv_gain: needs at least %d rows (shorter vectors are done on the host)", kGT);
+    const size_t smem = ((size_t)2 * n + 96 + 4) * sizeof(double);
+    int dev = 0, optin = 0;
+    SHG_CHECK(cudaGetDevice(&dev));
+    SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SHG_REQUIRE((int)smem <= optin, "shg_transv_gain: %d rows do not fit shared memory", n);
+    SHG_CHECK(cudaFuncSetAttribute(transv_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transv_gain_kernel<<<n_imgs, kGT, smem, as_stream(stream)>>>(d_stats, n, window, d_coeffs, d_taper, y1, n_rows,
+                                                                d_gains);
     SHG_LAUNCH_CHECK();
     return 0;
 }

@@ -513,7 +513,7 @@ class Engine:
             xb.append(math.floor(min(cx + dx, borders[2])))
         return y1, y2, np.asarray(rows, np.int32), np.asarray(xa, np.int32), np.asarray(xb, np.int32)
 
-    def transversalium_row_stats(self, imgs, rows, xa, xb):
+    def transversalium_row_stats(self, imgs, rows, xa, xb, device: bool = False):
         """Per-row robust mean of log(img[y]/img[y-1]) over [xa, xb) (solex_util.py:392-395)
         for one (h, w) image -> (n,), or a (S, h, w) batch sharing the chords -> (S, n).
         One launch, one device -> host copy."""
@@ -536,8 +536,34 @@ class Engine:
              idx[1].data_ptr(), idx[2].data_ptr(), n, max_len, self.logtab.data_ptr(), out.data_ptr(),
              _ptr(work), wb, self.stream)
         self.n_launches += 1
+        if device:
+            return out
         res = out.cpu().numpy()
         return res[0] if single else res
+
+    def transversalium_gains(self, stats_dev, y1: int, y2: int, n_rows: int, strength: int):
+        """(S, n_rows) device tensor of per-row gains from the (S, n-1) device row
+        statistics (solex_util.py:400-404, 456-479).  Vectors too short for the
+        kernel (a Sun < 256 rows) go through the same arithmetic on the host."""
+        from .solex_util import savgol_window, transversalium_gains, tukey_taper
+        n = y2 - y1
+        window = savgol_window(n, strength)
+        if n < 256 or window < 5:
+            g = transversalium_gains(stats_dev.cpu().numpy(), y1, y2, n_rows, strength)
+            return torch.from_numpy(g).to(self.device)
+        from scipy.signal import savgol_coeffs
+        key = (n, window)
+        if getattr(self, '_gain_tab_key', None) != key:
+            tab = np.concatenate([savgol_coeffs(window, 3), tukey_taper(n)])
+            self._gain_tab = torch.from_numpy(tab).to(self.device)
+            self._gain_tab_key = key
+        n_imgs = stats_dev.shape[0]
+        assert stats_dev.shape[1] == n - 1 and stats_dev.is_contiguous()
+        gains = self.empty((n_imgs, n_rows), torch.float64)
+        call('shg_transv_gain', stats_dev.data_ptr(), n_imgs, n, window, self._gain_tab.data_ptr(),
+             self._gain_tab[window:].data_ptr(), int(y1), int(n_rows), gains.data_ptr(), self.stream)
+        self.n_launches += 1
+        return gains
 
     def row_scale(self, imgs, gain, out=None):
         """(img.T * c).T, clip 65535, truncate (solex_util.py:489,515-516) for one

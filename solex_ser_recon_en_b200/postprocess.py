@@ -92,18 +92,17 @@ def _stack_rows(eng, images):
 def detransversalium_many(images, circle, borders, strength):
     """Transversalium correction of several row-major device images that share
     the disk geometry.  Returns (list of DeviceImage, gains (S, rows))."""
-    from .solex_util import transversalium_gains
     eng = get_engine()
     if not images:
         return [], np.zeros((0, 0))
     batch = _stack_rows(eng, images)
     y1, y2, rows, xa, xb = eng.transversalium_chords(circle, borders)
     with eng.stage('transv_stats'):
-        stats = eng.transversalium_row_stats(batch, rows, xa, xb)
+        stats = eng.transversalium_row_stats(batch, rows, xa, xb, device=True)
     h = batch.shape[1]
-    with eng.stage('transv_gain_host'):
-        gains = transversalium_gains(stats, y1, y2, h, strength)
-        gains_d = torch.from_numpy(gains).to(eng.device)
+    with eng.stage('transv_gain'):
+        gains_d = eng.transversalium_gains(stats, y1, y2, h, strength)
     with eng.stage('row_scale'):
         out = eng.row_scale(batch, gains_d)
+    gains = gains_d.cpu().numpy()                    # options['_transversalium_cache'] is a host array upstream
     return [DeviceImage(eng, out[i]) for i in range(len(images))], gains

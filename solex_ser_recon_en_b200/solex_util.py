@@ -293,6 +293,11 @@ def transversalium_gain(y_ratios_r, y1, y2, n_rows, strength):
     return c
 
 
+def savgol_window(n, strength):
+    """Window of the trend filter for n rows (solex_util.py:400)."""
+    return min(strength, n // 2 * 2 - 1)
+
+
 def savgol_cubic_rows(x, window):
     """scipy.signal.savgol_filter(x, window, 3, axis=-1) (mode 'interp') for a
     (S, n) batch in O(S*n): the smoothing weights of a local cubic fit are
@@ -336,7 +341,7 @@ def transversalium_gains(stats, y1, y2, n_rows, strength):
     s = stats.shape[0]
     ratios = np.concatenate([np.zeros((s, 1)), stats], axis=1)           # y_ratios_r[0] = 0 (solex_util.py:386)
     n = ratios.shape[1]
-    trend = savgol_cubic_rows(ratios, min(strength, n // 2 * 2 - 1))
+    trend = savgol_cubic_rows(ratios, savgol_window(n, strength))
     detrended = ratios - trend
     detrended -= np.mean(detrended, axis=1, keepdims=True)
     correction = np.exp(-np.cumsum(detrended, axis=1))

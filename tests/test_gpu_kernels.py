@@ -483,3 +483,17 @@ def test_limb_building_blocks(eng):
     lo, hi = eng.blur_range(box, scale, ceiling)
     assert ((lo * 2.0 ** -20) * scale, (hi * 2.0 ** -20) * scale) == (data.min(), data.max())
     assert np.array_equal(eng.blur_hist(box, scale, ceiling, edges), counts)
+
+
+@pytest.mark.parametrize('n,strength', [(3276, 301), (700, 301), (300, 301), (256, 301), (257, 9)])
+def test_gain_kernel_matches_reference_arithmetic(eng, n, strength):
+    """savgol trend + detrend + exp(-cumsum) + taper on the device against the
+    oracle's scipy / numpy version of the same lines (tolerance: north_star's 1e-5; measured ~1e-12)."""
+    import torch
+    rng = np.random.default_rng(n)
+    stats = rng.normal(0, 2e-3, (5, n - 1)) + 1e-3 * np.sin(np.arange(n - 1) / 40.0)
+    y1, n_rows = 37, n + 100
+    g = eng.transversalium_gains(torch.from_numpy(stats).to(eng.device), y1, y1 + n, n_rows, strength).cpu().numpy()
+    for i in range(stats.shape[0]):
+        want = O.transversalium_gain(np.concatenate([[0.0], stats[i]]), y1, y1 + n, n_rows, strength)
+        np.testing.assert_allclose(g[i], want, rtol=1e-9)
