@@ -90,15 +90,28 @@ int shg_fit_table(const double* d_coef, int ih, double* d_fit /* ih x 4 */, void
  *   disk[s][k][i] = trunc(L*lw + R*rw), L/R = img_k[i][il], img_k[i][il+1]
  *   lw = 1 - fit[i][1], rw = 1 - lw   (fp64, separate mul/mul/add)
  * 8-bit input is scaled by 256.  h_fit is the HOST (ih x 4) fit table exactly
- * as read_video_improved receives it.  d_disk is frame-major; element (s,k,i)
- * lives at d_disk[s*shift_stride + (k0_out+k)*ih + i].  d_work: device scratch
- * of at least shg_recon_workspace_bytes(ih, n_shifts) bytes.
- * impl: 0 = auto, 1 = generic direct-load kernel, 2 = TMA band kernel. */
+ * as read_video_improved receives it.  Disks are frame-major; element (s,k,i)
+ * lives at image_s[(k0_out+k)*ih + i], where image_s = d_disk + s*shift_stride,
+ * or, when h_out_ptrs (HOST array of n_shifts device addresses) is given,
+ * image_s = h_out_ptrs[s]: the images may then live on PEER GPUs (addresses
+ * from shg_ipc_open), so each rank writes its frame rows straight into the
+ * owner's image over NVLink -- reconstruction and the row exchange are one
+ * kernel.  d_work: device scratch of at least shg_recon_workspace_bytes(ih,
+ * n_shifts) bytes.  impl: 0 = auto, 1 = generic direct-load kernel, 2 = TMA
+ * band kernel. */
 int64_t shg_recon_workspace_bytes(int ih, int n_shifts);
 int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
               const double* h_fit, const int32_t* h_shifts, int n_shifts,
-              uint16_t* d_disk, int64_t shift_stride, int64_t k0_out, int impl,
+              uint16_t* d_disk, int64_t shift_stride, const uint64_t* h_out_ptrs, int64_t k0_out, int impl,
               void* d_work, int64_t work_bytes, void* stream);
+
+/* ---- multi-GPU row exchange: device buffers other ranks of the box can write
+ * (cudaMalloc + CUDA IPC; handles travel through torch.distributed) -------- */
+#define SHG_IPC_HANDLE_BYTES 64
+int shg_ipc_alloc(int64_t bytes, void** d_ptr, unsigned char* handle64);
+int shg_ipc_free(void* d_ptr);
+int shg_ipc_open(const unsigned char* handle64, void** d_ptr);   /* enables peer access lazily */
+int shg_ipc_close(void* d_ptr);
 
 /* ---- layout helpers ------------------------------------------------------ */
 /* out[c][r'] = in[r][c] for in of shape (rows, cols); flip != 0 reverses the

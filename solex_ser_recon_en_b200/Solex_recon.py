@@ -36,8 +36,6 @@ def solex_do_work(tasks, flag_command_line=False):
         for file, options in tasks:
             print('file %s is processing' % file)
             disk_list, backup_bounds, hdr = solex_read(file, options)
-            if parallel.world()[0] != 0:
-                continue                                     # rows were gathered to rank 0
             pending += solex_process(options, disk_list, backup_bounds, hdr, _pool=pool)
         for fut in pending:
             fut.result()
@@ -64,6 +62,8 @@ def solex_read_reader(rdr, options, basefich0):
     disk_list, ih, iw, _ = read_video_improved(rdr, fit, options)
     hdr['NAXIS1'] = iw
     for i in range(len(disk_list)):
+        if disk_list[i] is None:                              # image owned by another rank
+            continue
         if options['flip_x']:
             disk_list[i] = disk_list[i].flipped() if isinstance(disk_list[i], DeviceImage) \
                 else np.flip(disk_list[i], axis=1)
@@ -94,12 +94,18 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
     borders = [0, 0, 0, 0]
     cercle0 = (-1, -1, -1)
     shifts = options['shift']
-    requested = [i for i in range(len(disk_list)) if shifts[i] in options['shift_requested']]
+    # with several ranks each one post-processes the shifts whose images it owns
+    requested = [i for i in range(len(disk_list))
+                 if shifts[i] in options['shift_requested'] and disk_list[i] is not None]
     circular = {}
-    # 1. geometry: disk_list[0] is the ellipse-fit shift; the fit is made once and reused
+    # 1. geometry: disk_list[0] is the ellipse-fit shift; the fit is made once (by its owner) and reused
     if options['ratio_fixe'] is None and options['slant_fix'] is None:
-        basefich = basefich0 + '_shift=' + str(shifts[0])
-        circular[0], cercle0, options['ratio_fixe'], phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+        geom = None
+        if disk_list[0] is not None:
+            basefich = basefich0 + '_shift=' + str(shifts[0])
+            circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+            geom = (tuple(float(v) for v in cercle0), float(ratio_fit), float(phi), [float(b) for b in borders])
+        cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_object(geom, src=0)
         options['slant_fix'] = math.degrees(phi)
         todo = [i for i in requested if i != 0]
     else:

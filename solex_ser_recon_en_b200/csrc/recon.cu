@@ -35,6 +35,7 @@ struct ShiftTable {
     int run_first[kMaxRuns + 1];   // [run] -> first index into sh/slot (sorted by shift)
     int run_rows[kMaxRuns];        // TMA box height of the run
     int run_off[kMaxRuns];         // element offset of the run inside one stage
+    int run_unit[kMaxRuns];        // 1 when the run's shifts are consecutive integers
     short sh[kMaxShifts];
     short slot[kMaxShifts];        // output image index of sh[j]
 };
@@ -50,6 +51,11 @@ __device__ __forceinline__ double px_to_double<uint16_t>(uint16_t v) { return u3
 template <>
 __device__ __forceinline__ double px_to_double<uint8_t>(uint8_t v) { return u32_to_double((uint32_t)v << 8); }
 
+// 16-bit store to a global address held as an integer (local HBM or a peer GPU's)
+__device__ __forceinline__ void st_global_u16(unsigned long long addr, uint16_t v) {
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"(v) : "memory");
+}
+
 __device__ __forceinline__ uint16_t lerp_trunc(double L, double R, double lw, double rw) {
     // (L*lw) + (R*rw), each rounded to nearest: no fma contraction
     return (uint16_t)double_floor_to_u32(__dadd_rn(__dmul_rn(L, lw), __dmul_rn(R, rw)));
@@ -60,7 +66,7 @@ template <typename T, bool ROT>
 __global__ void __launch_bounds__(256)
 recon_generic_kernel(const T* __restrict__ frames, int64_t n_frames, int W, int H,
                      const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
-                     const __grid_constant__ ShiftTable tab, uint16_t* __restrict__ disk, int64_t shift_stride,
+                     const __grid_constant__ ShiftTable tab, const unsigned long long* __restrict__ out_ptrs,
                      int64_t k0_out) {
     const int ih = ROT ? W : H, iw = ROT ? H : W;
     const int t = blockIdx.x * 256 + threadIdx.x;
@@ -70,7 +76,7 @@ recon_generic_kernel(const T* __restrict__ frames, int64_t n_frames, int W, int 
     const double wl = lw[i], wr = rw[i];
     for (int64_t k = blockIdx.y; k < n_frames; k += gridDim.y) {
         const T* fr = frames + k * (int64_t)H * W;
-        uint16_t* out = disk + (k0_out + k) * ih + i;
+        const int64_t off = (k0_out + k) * ih + i;
         for (int j = 0; j < tab.n_shifts; ++j) {
             const int il = min(max(f + tab.sh[j], 0), iw - 2);
             T a, b;
@@ -81,7 +87,7 @@ recon_generic_kernel(const T* __restrict__ frames, int64_t n_frames, int W, int 
                 a = fr[(int64_t)t * W + il];
                 b = fr[(int64_t)t * W + il + 1];
             }
-            out[tab.slot[j] * shift_stride] = lerp_trunc(px_to_double<T>(a), px_to_double<T>(b), wl, wr);
+            st_global_u16(out_ptrs[j] + (unsigned long long)(off * 2), lerp_trunc(px_to_double<T>(a), px_to_double<T>(b), wl, wr));
         }
     }
 }
@@ -126,11 +132,13 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
                  int64_t n_frames, int W, int H, int n_tx, int stage_elems,
                  const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
                  const int* __restrict__ row0 /* [n_tx][n_runs] */,
-                 uint16_t* __restrict__ disk, int64_t shift_stride, int64_t k0_out) {
+                 const unsigned long long* __restrict__ out_ptrs, int64_t k0_out) {
     extern __shared__ unsigned char smem_raw[];
     // TMA destinations want 128-byte alignment; the launch reserves the slack
     T* stage_buf = reinterpret_cast<T*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ unsigned long long s_out[kMaxShifts];      // per-shift output image (local or a peer GPU's)
+    for (int j = threadIdx.x; j < tab.n_shifts; j += blockDim.x) s_out[j] = out_ptrs[j];
 
     const int tid = threadIdx.x;
     const int col = tid % TX, grp = tid / TX;
@@ -178,22 +186,38 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
 
         if (live) {
             const T* buf = stage_buf + (size_t)stage * stage_elems + col;
-            uint16_t* out = disk + (k0_out + k) * W + i;
+            const unsigned long long off2 = (unsigned long long)(((k0_out + k) * W + i) * 2);   // byte offset
             for (int r = 0; r < tab.n_runs; ++r) {
                 const T* rb = buf + tab.run_off[r];
                 const int base = row0[tx * tab.n_runs + r];
                 const int ja = tab.run_first[r], jb = tab.run_first[r + 1];
                 const int per = (jb - ja + G - 1) / G;
                 const int j0 = ja + grp * per, j1 = min(jb, j0 + per);
-                int prev = -0x40000000;
-                double R = 0.0;
+                if (j0 >= j1) continue;
+                const int first_il = f + tab.sh[j0];
+                if (tab.run_unit[r] && first_il >= 0 && first_il + (j1 - 1 - j0) <= iw - 2) {
+                    // consecutive shifts, nothing clipped: walk down the band one row per shift;
+                    // each tap is loaded and converted once (right tap of shift s = left tap of s+1)
+                    const T* p = rb + (first_il - base) * TX;
+                    double Lw = __dmul_rn(px_to_double<T>(p[0]), wl);
 #pragma unroll 4
-                for (int j = j0; j < j1; ++j) {
-                    const int il = min(max(f + tab.sh[j], 0), iw - 2) - base;
-                    const double L = (il == prev + 1) ? R : px_to_double<T>(rb[il * TX]);
-                    R = px_to_double<T>(rb[(il + 1) * TX]);
-                    prev = il;
-                    out[tab.slot[j] * shift_stride] = lerp_trunc(L, R, wl, wr);
+                    for (int j = j0; j < j1; ++j) {
+                        p += TX;
+                        const double R = px_to_double<T>(p[0]);
+                        const double v = __dadd_rn(Lw, __dmul_rn(R, wr));
+                        Lw = __dmul_rn(R, wl);
+                        st_global_u16(s_out[j] + off2, (uint16_t)double_floor_to_u32(v));
+                    }
+                } else {
+                    int prev = -0x40000000;
+                    double R = 0.0;
+                    for (int j = j0; j < j1; ++j) {
+                        const int il = min(max(f + tab.sh[j], 0), iw - 2) - base;
+                        const double L = (il == prev + 1) ? R : px_to_double<T>(rb[il * TX]);
+                        R = px_to_double<T>(rb[(il + 1) * TX]);
+                        prev = il;
+                        st_global_u16(s_out[j] + off2, lerp_trunc(L, R, wl, wr));
+                    }
                 }
             }
         }
@@ -258,6 +282,11 @@ void build_runs(const int32_t* shifts, int n, int max_rows, ShiftTable& tab, std
     tab.n_runs = (int)firsts.size();
     for (int r = 0; r < tab.n_runs; ++r) tab.run_first[r] = firsts[r];
     tab.run_first[tab.n_runs] = n;
+    for (int r = 0; r < tab.n_runs; ++r) {
+        tab.run_unit[r] = 1;
+        for (int j = tab.run_first[r] + 1; j < tab.run_first[r + 1]; ++j)
+            if (order[j].first != order[j - 1].first + 1) tab.run_unit[r] = 0;
+    }
 }
 
 }  // namespace
@@ -268,13 +297,13 @@ extern "C" int64_t shg_recon_workspace_bytes(int ih, int n_shifts) {
     const int64_t b = ((int64_t)ih * 8 + 255) / 256 * 256;
     const int64_t c = (((int64_t)(ih + 63) / 64) * kMaxRuns * 4 + 255) / 256 * 256;
     (void)n_shifts;
-    return a + 2 * b + c;
+    return a + 2 * b + c + kMaxShifts * 8;
 }
 
 extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
                          const double* h_fit, const int32_t* h_shifts, int n_shifts,
-                         uint16_t* d_disk, int64_t shift_stride, int64_t k0_out, int impl,
-                         void* d_work, int64_t work_bytes, void* stream) {
+                         uint16_t* d_disk, int64_t shift_stride, const uint64_t* h_out_ptrs, int64_t k0_out,
+                         int impl, void* d_work, int64_t work_bytes, void* stream) {
     SHG_REQUIRE(bytes_per_px == 1 || bytes_per_px == 2, "shg_recon: bytes_per_px must be 1 or 2");
     SHG_REQUIRE(n_shifts >= 1 && n_shifts <= kMaxShifts, "shg_recon: %d shifts (max %d)", n_shifts, kMaxShifts);
     SHG_REQUIRE(W >= 2 && H >= 2, "shg_recon: bad geometry %dx%d", W, H);
@@ -361,6 +390,17 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     double* d_lw = reinterpret_cast<double*>(w + a);
     double* d_rw = reinterpret_cast<double*>(w + a + b);
     int* d_row0 = reinterpret_cast<int*>(w + a + 2 * b);
+    const int64_t c_bytes = (((int64_t)(ih + 63) / 64) * kMaxRuns * 4 + 255) / 256 * 256;
+    unsigned long long* d_optr = reinterpret_cast<unsigned long long*>(w + a + 2 * b + c_bytes);
+    // output image of each shift, in the kernels' sorted shift order
+    std::vector<unsigned long long> optr(n_shifts);
+    for (int j = 0; j < n_shifts; ++j) {
+        const int slot = plan.tab.slot[j];
+        optr[j] = h_out_ptrs ? (unsigned long long)h_out_ptrs[slot]
+                             : (unsigned long long)(uintptr_t)(d_disk + (int64_t)slot * shift_stride);
+        SHG_REQUIRE(optr[j] != 0 && optr[j] % 2 == 0, "shg_recon: bad output pointer for shift slot %d", slot);
+    }
+    SHG_CHECK(cudaMemcpyAsync(d_optr, optr.data(), (size_t)n_shifts * 8, cudaMemcpyHostToDevice, st));
     SHG_CHECK(cudaMemcpyAsync(d_fl, plan.fl.data(), (size_t)ih * 4, cudaMemcpyHostToDevice, st));
     SHG_CHECK(cudaMemcpyAsync(d_lw, plan.lw.data(), (size_t)ih * 8, cudaMemcpyHostToDevice, st));
     SHG_CHECK(cudaMemcpyAsync(d_rw, plan.rw.data(), (size_t)ih * 8, cudaMemcpyHostToDevice, st));
@@ -368,13 +408,13 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     if (!tma) {
         dim3 grid((ih + 255) / 256, (unsigned)std::min<int64_t>(n_frames, 65535));
         if (rot && bytes_per_px == 2)
-            recon_generic_kernel<uint16_t, true><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+            recon_generic_kernel<uint16_t, true><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_optr, k0_out);
         else if (rot)
-            recon_generic_kernel<uint8_t, true><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+            recon_generic_kernel<uint8_t, true><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_optr, k0_out);
         else if (bytes_per_px == 2)
-            recon_generic_kernel<uint16_t, false><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+            recon_generic_kernel<uint16_t, false><<<grid, 256, 0, st>>>((const uint16_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_optr, k0_out);
         else
-            recon_generic_kernel<uint8_t, false><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_disk, shift_stride, k0_out);
+            recon_generic_kernel<uint8_t, false><<<grid, 256, 0, st>>>((const uint8_t*)d_frames, n_frames, W, H, d_fl, d_lw, d_rw, plan.tab, d_optr, k0_out);
         SHG_LAUNCH_CHECK();
         return 0;
     }
@@ -412,7 +452,7 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
         auto kern = recon_tma_kernel<T, TXV, ST, GV>;                                                      \
         SHG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         kern<<<grid, TXV * GV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, d_fl, \
-                                           d_lw, d_rw, d_row0, d_disk, shift_stride, k0_out);              \
+                                           d_lw, d_rw, d_row0, d_optr, k0_out);                            \
     } while (0)
 #define SHG_DISPATCH_G(T, TXV, ST)                                           \
     do {                                                                     \

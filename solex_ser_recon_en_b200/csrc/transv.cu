@@ -229,28 +229,150 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path for chords of at most 32 elements per thread (n <= 32*kT): the
+// order statistic is found by a binary MSB-first radix select on monotone
+// 32-bit keys (the float32 rounding of the fp64 key, order-preserving bit
+// transform) held BIT-SLICED in registers: after a 32x32 bit transpose,
+// slice[b] holds bit b of each of the thread's 32 keys, so one level is two
+// logic ops + a popcount per thread and one block-wide sum.  float32 rounding is
+// monotone, so keys strictly below the target key are strictly below in fp64;
+// the (usually single) elements that share the final key are ranked exactly in
+// fp64.  Ranks t and t+1 (even n) share the descent until they part ways.
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+    // afterwards a[i] bit j == (old a[j]) bit i
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= t << j;
+            a[k + j] ^= t;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t ordered_key32(double x) {
+    const uint32_t b = __float_as_uint(__double2float_rn(x));
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+template <int kT>
+__device__ __forceinline__ int block_sum_int(int v, Shared& S) {
+    constexpr int NW = kT / 32;
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) S.hist[threadIdx.x >> 5] = (unsigned int)v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += (int)S.hist[w];
+    return t;
+}
+
+// Returns true when handled (results in S.dbc[0..1]); false -> caller falls back to block_select.
+template <int KIND, int kT>
+__device__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
+    uint32_t a[32];
+    uint32_t cand = 0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int i = e * kT + (int)threadIdx.x;
+        a[e] = 0;
+        if (i < n) {
+            const double x = key_of<KIND>(vals, i, med);
+            if (fabs(x) < INFINITY) {                           // +-inf are ranked by the caller
+                a[e] = ordered_key32(x);
+                cand |= 1u << e;
+            }
+        }
+    }
+    transpose32(a);
+    bool split = false;
+    uint32_t lo_set = 0, hi_set = 0;
+#pragma unroll
+    for (int L = 0; L < 32; ++L) {
+        const uint32_t slice = a[31 - L];
+        const int Z = block_sum_int<kT>(__popc(cand & ~slice), S);
+        if (need2 && t == Z - 1) {                             // rank t is the largest "0", rank t+1 the smallest "1"
+            lo_set = cand & ~slice;
+            hi_set = cand & slice;
+            split = true;
+            break;
+        }
+        if (t < Z) cand &= ~slice;
+        else { t -= Z; cand &= slice; }
+    }
+    if (split) {
+        double v0 = -INFINITY, v1 = INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int i = e * kT + (int)threadIdx.x;
+            if ((lo_set >> e) & 1u) v0 = fmax(v0, key_of<KIND>(vals, i, med));
+            if ((hi_set >> e) & 1u) v1 = fmin(v1, key_of<KIND>(vals, i, med));
+        }
+        block_minmax(v1, v0, S);
+        if (threadIdx.x == 0) { S.dbc[0] = v0; S.dbc[1] = v1; }
+        __syncthreads();
+        return true;
+    }
+    // every remaining candidate has the same 32-bit key: rank them exactly
+    if (threadIdx.x == 0) S.list_n = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        if ((cand >> e) & 1u) {
+            const int slot = atomicAdd(&S.list_n, 1);
+            if (slot < kListCap) S.list[slot] = key_of<KIND>(vals, e * kT + (int)threadIdx.x, med);
+        }
+    }
+    __syncthreads();
+    const int m = S.list_n;
+    if (m > kListCap) return false;                            // very many near-identical values: generic path
+    for (int c = threadIdx.x; c < m; c += kT) {
+        const double x = S.list[c];
+        int rank = 0;
+        for (int i = 0; i < m; ++i) {
+            const double o = S.list[i];
+            rank += (o < x || (o == x && i < c)) ? 1 : 0;
+        }
+        if (rank == t) S.dbc[0] = x;
+        if (rank == t + 1) S.dbc[1] = x;
+    }
+    __syncthreads();
+    if (!need2 && threadIdx.x == 0) S.dbc[1] = S.dbc[0];
+    __syncthreads();
+    return true;
+}
+
 // value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
 template <int KIND, int kT>
 __device__ void ranked_pair(const double* vals, int n, double med, double lo, double hi, int nneg, int nfin,
                             int t0, int t1, double& v0, double& v1, Shared& S) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
+    const bool small = n <= 32 * kT;
+    auto select = [&](int t, bool need2) {
+        if (!(small && fast_select<KIND, kT>(vals, n, med, t, need2, S)))
+            block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t, need2, S);
+    };
     if (g0 == 0 && g1 == 0) {
-        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
+        select(t0 - nneg, t1 != t0);
         v0 = S.dbc[0];
         v1 = S.dbc[1];
         __syncthreads();
         return;
     }
     if (g0 == 0) {
-        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, false, S);
+        select(t0 - nneg, false);
         v0 = S.dbc[0];
         __syncthreads();
     } else {
         v0 = g0 < 0 ? -INFINITY : INFINITY;
     }
     if (g1 == 0) {
-        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t1 - nneg, false, S);
+        select(t1 - nneg, false);
         v1 = S.dbc[0];
         __syncthreads();
     } else {
@@ -515,7 +637,7 @@ extern "C" int shg_log_table(double* d_tab65536, void* stream) {
 
 static int transv_threads(int max_len) {
     // enough threads that each owns <= ~32 elements, few enough that several rows share an SM
-    return max_len <= 4096 ? 128 : (max_len <= 12288 ? 512 : 1024);
+    return max_len <= 4096 ? 128 : (max_len <= 16384 ? 512 : 1024);
 }
 
 static int64_t transv_smem_cap(int optin) {

@@ -35,7 +35,6 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     const int img = blockIdx.z;
     const uint16_t* disk = disk_base + (int64_t)(sel ? sel[img] : img) * disk_stride;
     uint16_t* out = out_base + (int64_t)img * out_stride;
-    const double lo = (double)minmax[2 * img], hi = (double)minmax[2 * img + 1];
     const double cval = u32_to_double(disk[(flip ? (n_frames - 1) : 0) * (int64_t)ih]);   // image[0][0]
     const int r0 = blockIdx.y * kRows;
     const int c0 = blockIdx.x * COLS;
@@ -60,18 +59,40 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     const int64_t kend = min((int64_t)ceil(xb) + 1, kbase + span);   // exclusive
     const int nrow = min(r1, ih) - r0;                                // valid slit rows (may be <= 0)
     // ---- stage: coalesced along the slit axis (64 rows = 128 B per frame) ----
-    for (int64_t kk = kbase + (threadIdx.x >> 5); kk < kend; kk += 8) {
-        uint16_t* dst = tile + (kk - kbase) * kPitch;
-        if (kk < 0 || kk >= n_frames) continue;                        // never read (range test below)
-        const int64_t ksrc = flip ? (n_frames - 1 - kk) : kk;
-        const uint16_t* src = disk + ksrc * ih + r0;
-        for (int j = (threadIdx.x & 31) * 2; j < nrow; j += 64) {
-            if (j + 1 < nrow && (((uintptr_t)(src + j)) & 3) == 0) {
-                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + j);
-                *reinterpret_cast<uint32_t*>(dst + j) = v;
-            } else {
-                dst[j] = src[j];
-                if (j + 1 < nrow) dst[j + 1] = src[j + 1];
+    const int n_stage = (int)(kend - kbase);
+    if (nrow == kRows && (ih & 7) == 0 && (((uintptr_t)disk) & 15) == 0) {
+        // 16-byte loads: 8 lanes cover one frame's 64 rows, a warp takes 4 frames per instruction
+        const int seg = threadIdx.x & 7;
+        for (int f = threadIdx.x >> 3; f < n_stage; f += 64) {          // two frames in flight per thread
+            const int f2 = f + 32;
+            const int64_t k0 = kbase + f, k1 = kbase + f2;
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+            const bool ok0 = k0 >= 0 && k0 < n_frames, ok1 = f2 < n_stage && k1 >= 0 && k1 < n_frames;
+            if (ok0) v0 = ld_stream_u4(reinterpret_cast<const uint4*>(disk + (flip ? (n_frames - 1 - k0) : k0) * ih + r0) + seg);
+            if (ok1) v1 = ld_stream_u4(reinterpret_cast<const uint4*>(disk + (flip ? (n_frames - 1 - k1) : k1) * ih + r0) + seg);
+            if (ok0) {
+                uint32_t* d = reinterpret_cast<uint32_t*>(tile + f * kPitch + seg * 8);
+                d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
+            }
+            if (ok1) {
+                uint32_t* d = reinterpret_cast<uint32_t*>(tile + f2 * kPitch + seg * 8);
+                d[0] = v1.x; d[1] = v1.y; d[2] = v1.z; d[3] = v1.w;
+            }
+        }
+    } else {
+        for (int64_t kk = kbase + (threadIdx.x >> 5); kk < kend; kk += 8) {
+            uint16_t* dst = tile + (kk - kbase) * kPitch;
+            if (kk < 0 || kk >= n_frames) continue;                        // never read (range test below)
+            const int64_t ksrc = flip ? (n_frames - 1 - kk) : kk;
+            const uint16_t* src = disk + ksrc * ih + r0;
+            for (int j = (threadIdx.x & 31) * 2; j < nrow; j += 64) {
+                if (j + 1 < nrow && (((uintptr_t)(src + j)) & 3) == 0) {
+                    const uint32_t v = *reinterpret_cast<const uint32_t*>(src + j);
+                    *reinterpret_cast<uint32_t*>(dst + j) = v;
+                } else {
+                    dst[j] = src[j];
+                    if (j + 1 < nrow) dst[j + 1] = src[j + 1];
+                }
             }
         }
     }
@@ -80,18 +101,26 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     const int c = c0 + (threadIdx.x % COLS);
     if (c >= out_cols) return;
     const double mc = __dmul_rn(m00, (double)c);
+    const int ilo = (int)minmax[2 * img], ihi = (int)minmax[2 * img + 1];
+    const int kb = (int)kbase, nf = (int)n_frames;
+    constexpr double kMagic = 6755399441055744.0;                      // 1.5 * 2^52: x + kMagic holds floor(x) in its low word
     for (int r = r0 + threadIdx.x / COLS; r < r1; r += RGROUPS) {
         const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
-        const double xf = floor(x), xc = ceil(x);
-        const double d = __dsub_rn(x, xf);
+        const double xm = __dadd_rd(x, kMagic);
+        const int kf = __double2loint(xm);                              // floor(x) (|x| < 2^31)
+        const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));          // x - floor(x), exact subtraction of the integer
+        const int kc = kf + (d != 0.0 ? 1 : 0);                         // ceil(x)
         double L = cval, R = cval;
         if (r < ih) {
-            if (xf >= 0.0 && xf < (double)n_frames) L = u32_to_double(tile[((int64_t)xf - kbase) * kPitch + (r - r0)]);
-            if (xc >= 0.0 && xc < (double)n_frames) R = u32_to_double(tile[((int64_t)xc - kbase) * kPitch + (r - r0)]);
+            const uint16_t* col = tile + (r - r0);
+            if (kf >= 0 && kf < nf) L = u32_to_double(col[(kf - kb) * kPitch]);
+            if (kc >= 0 && kc < nf) R = u32_to_double(col[(kc - kb) * kPitch]);
         }
-        double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
-        v = fmin(fmax(v, lo), hi);
-        out[(int64_t)r * out_cols + c] = (uint16_t)double_floor_to_u32(v);
+        const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
+        // trunc(clip(v, lo, hi)) == clamp(floor(v), lo, hi) because lo and hi are integers
+        int q = __double2loint(__dadd_rd(v, kMagic));
+        q = min(max(q, ilo), ihi);
+        out[(int64_t)r * out_cols + c] = (uint16_t)q;
     }
 }
 

@@ -329,13 +329,26 @@ class Engine:
         return self.empty((n_shifts, n_frames, ih), torch.uint16)
 
     def recon(self, stack: DeviceStack, fit: np.ndarray, shifts, disk=None, k0_out: int | None = None,
-              impl: int = 0):
+              impl: int = 0, out_ptrs=None):
         """disk[s, k, i] (frame-major) for the frames of `stack`; with `disk`
-        given the rows land at frame offset k0_out (default: the stack's k0)."""
+        given the rows land at frame offset k0_out (default: the stack's k0).
+        `out_ptrs` (one device address per shift, possibly on peer GPUs) replaces
+        `disk`: each shift's rows are written into that image at offset k0_out."""
         g = stack.geom
         shifts = np.ascontiguousarray(shifts, dtype=np.int32)
         fit = np.ascontiguousarray(fit, dtype=np.float64)
         assert fit.shape == (g.ih, 4)
+        if out_ptrs is not None:
+            ptrs = np.ascontiguousarray(out_ptrs, dtype=np.uint64)
+            assert len(ptrs) == len(shifts)
+            wb = int(lib.shg_recon_workspace_bytes(g.ih, len(shifts)))
+            if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
+                self._recon_ws = self.empty((wb,), torch.uint8)
+            call('shg_recon', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.width, g.height,
+                 fit.ctypes.data, shifts.ctypes.data, len(shifts), 0, 0, ptrs.ctypes.data,
+                 int(stack.k0 if k0_out is None else k0_out), int(impl), self._recon_ws.data_ptr(), wb, self.stream)
+            self.n_launches += 1
+            return None
         if disk is None:
             disk = self.alloc_disk(len(shifts), stack.n, g.ih)
             k0_out = 0
@@ -346,7 +359,7 @@ class Engine:
         if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
             self._recon_ws = self.empty((wb,), torch.uint8)
         call('shg_recon', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.width, g.height,
-             fit.ctypes.data, shifts.ctypes.data, len(shifts), disk.data_ptr(), disk.stride(0), int(k0_out),
+             fit.ctypes.data, shifts.ctypes.data, len(shifts), disk.data_ptr(), disk.stride(0), 0, int(k0_out),
              int(impl), self._recon_ws.data_ptr(), wb, self.stream)
         self.n_launches += 1
         return disk

@@ -45,6 +45,106 @@ def combine_stats(stack):
     return total_sum, total_max, stack.geom.n_frames
 
 
+def shift_owner(n_shifts: int, size: int | None = None, mode: str = 'by_shift'):
+    """Rank that ends up holding the complete image of each shift.
+    'by_shift': contiguous blocks of the shift list (index 0, the ellipse-fit
+    shift, always lands on rank 0), so circularisation / transversalium / output
+    of the 101 images spread over the ranks like the reference's Pool workers;
+    'gather0': every image on rank 0 (north_star's "rows are gathered to rank 0")."""
+    _, s = world()
+    size = s if size is None else size
+    if mode == 'gather0' or size == 1:
+        return [0] * n_shifts
+    return [min(size - 1, j * size // n_shifts) for j in range(n_shifts)]
+
+
+class _RawDeviceMemory:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 2}
+
+
+class RowExchange:
+    """Peer-writable images for one scan geometry.  Every rank allocates the
+    images it owns with cudaMalloc, publishes a CUDA IPC handle, and opens the
+    other ranks' allocations: the reconstruction kernel of rank g then writes
+    its frame rows [k0_g, k1_g) of EVERY shift straight into the owner's image
+    through NVLink peer stores -- there is no separate gather / all-to-all pass
+    and no staging copy."""
+
+    def __init__(self, n_shifts, n_frames, ih, mode):
+        import ctypes as C
+        from ._lib import call
+        self.eng = get_engine()
+        self.rank, self.size = world()
+        self.key = (n_shifts, n_frames, ih, mode)
+        self.owner = shift_owner(n_shifts, self.size, mode)
+        self.mine = [j for j in range(n_shifts) if self.owner[j] == self.rank]
+        self.image_bytes = n_frames * ih * 2
+        nbytes = max(1, len(self.mine)) * self.image_bytes
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        call('shg_ipc_alloc', nbytes, C.byref(ptr), handle)
+        self.ptr = int(ptr.value)
+        gathered = [None] * self.size
+        dist.all_gather_object(gathered, bytes(handle.raw))
+        self.bases = {}
+        self.opened = []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                self.bases[r] = self.ptr
+            else:
+                p = C.c_void_p()
+                call('shg_ipc_open', h, C.byref(p))
+                self.bases[r] = int(p.value)
+                self.opened.append(int(p.value))
+        local_index = {}
+        counts = [0] * self.size
+        for j in range(n_shifts):
+            local_index[j] = counts[self.owner[j]]
+            counts[self.owner[j]] += 1
+        self.ptrs = np.array([self.bases[self.owner[j]] + local_index[j] * self.image_bytes for j in range(n_shifts)],
+                             dtype=np.uint64)
+        raw = torch.as_tensor(_RawDeviceMemory(self.ptr, nbytes), device=self.eng.device)
+        self.images = raw.view(torch.uint16).view(max(1, len(self.mine)), n_frames, ih)
+
+    def close(self):
+        from ._lib import lib
+        for p in self.opened:
+            lib.shg_ipc_close(p)
+        self.opened = []
+        if self.ptr:
+            lib.shg_ipc_free(self.ptr)
+            self.ptr = 0
+
+
+_exchange = {}
+EXCHANGE_MODE = 'by_shift'
+
+
+def row_exchange(n_shifts, n_frames, ih, mode=None):
+    mode = mode or EXCHANGE_MODE
+    key = (n_shifts, n_frames, ih, mode)
+    ex = _exchange.get('current')
+    if ex is None or ex.key != key:
+        if ex is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            ex.close()
+        ex = RowExchange(n_shifts, n_frames, ih, mode)
+        _exchange['current'] = ex
+    return ex
+
+
+def release_exchange():
+    ex = _exchange.pop('current', None)
+    if ex is not None:
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        ex.close()
+
+
 def gather_rows(local_disk, n_frames: int, dst: int = 0):
     """Assemble the (n_shifts, N, ih) disk on rank `dst` from each rank's
     (n_shifts, n_local, ih) block of frame rows.  Returns the full tensor on
@@ -64,24 +164,45 @@ def gather_rows(local_disk, n_frames: int, dst: int = 0):
                 continue
             a, b = frame_range(n_frames, src, size)
             bufs[src] = torch.empty((n_shifts, b - a, ih), dtype=local_disk.dtype, device=local_disk.device)
-            ops.append(dist.P2POp(dist.irecv, bufs[src].view(torch.int16), src))
+            ops.append(dist.P2POp(dist.irecv, bufs[src].view(torch.uint8), src))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         for src, buf in bufs.items():
             a, b = frame_range(n_frames, src, size)
             full[:, a:b].copy_(buf)
         return full
-    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_disk.contiguous().view(torch.int16), dst)]):
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_disk.contiguous().view(torch.uint8), dst)]):
         w.wait()
     return None
 
 
 def reconstruct(stack, fit: np.ndarray, shifts):
-    """Disk images for the whole scan on rank 0 (every rank when single-GPU)."""
+    """Reconstruct this rank's frames at every shift.  Returns a list with one
+    frame-major (N, ih) device image per shift -- every image on a single GPU;
+    with several ranks, the images this rank owns and None for the others."""
     eng = get_engine()
-    local = eng.recon(stack, fit, shifts)
     rank, size = world()
     if size == 1:
-        return local
-    full = gather_rows(local, stack.geom.n_frames)
-    return full if rank == 0 else local
+        local = eng.recon(stack, fit, shifts)
+        return [local[i] for i in range(len(shifts))]
+    g = stack.geom
+    ex = row_exchange(len(shifts), g.n_frames, g.ih)
+    torch.cuda.synchronize()
+    dist.barrier()                         # owners are done reading the previous scan's images
+    eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0)
+    torch.cuda.synchronize()
+    dist.barrier()                         # every rank's rows have landed
+    out = [None] * len(shifts)
+    for n, j in enumerate(ex.mine):
+        out[j] = ex.images[n]
+    return out
+
+
+def broadcast_object(obj, src: int):
+    """Small Python object from one rank to all (ellipse geometry)."""
+    _, size = world()
+    if size == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]

@@ -57,7 +57,7 @@ def write_complete(path, options):
 
 
 def logme(path, options, s):
-    if '_nolog' in options:
+    if '_nolog' in options or int(os.environ.get('RANK', '0')) != 0:     # one log per scan: rank 0 writes it
         return
     _append(path, options, s + '\n', 'a')
 
@@ -257,8 +257,9 @@ def read_video_improved(rdr, fit, options):
     from . import parallel
     with eng.stage('recon+gather'):
         disk = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts)
-    disk_list = [DeviceImage(eng, disk[i], 'frames') for i in range(len(shifts))]
-    if options['flag_display']:
+    # one image per shift; under several ranks only the images this rank owns (None elsewhere)
+    disk_list = [None if d is None else DeviceImage(eng, d, 'frames') for d in disk]
+    if options['flag_display'] and disk_list[1] is not None:
         cv2.namedWindow('disk', cv2.WINDOW_NORMAL)
         cv2.imshow('disk', np.asarray(disk_list[1]))             # disk_list[1] is always shift = 0
         if cv2.waitKey(1) == 27:
