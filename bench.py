@@ -13,7 +13,8 @@ frames are sharded by frame range across the ranks (strong scaling).
 
 One step = one pass of the whole path over the scan:
   value : stack already resident in HBM (pass 1 re-reads it) -> mean/max -> all-reduce -> line detection + fit
-          -> reconstruction at 101 shifts -> gather to rank 0 -> ellipse fit -> warp + transversalium per shift.
+          -> reconstruction at 101 shifts, each rank writing its frame rows into the owner rank's image over NVLink
+          -> ellipse fit (rank 0, broadcast) -> warp + transversalium of the shifts each rank owns.
   e2e   : the same through the public entry points (Solex_recon.solex_read_reader / solex_process) starting from the
           payload in pinned HOST memory (H2D inside the timed region, overlapped with pass 1) and ending with the
           final images copied back to pinned host memory (D2H inside the timed region).
@@ -243,14 +244,13 @@ def run_b200(a):
         opt['_result_sink'] = sink
         results.clear()
         disk_list, bounds, hdr = Solex_recon.solex_read_reader(reader, opt, 'bench')
-        if rank == 0:
-            Solex_recon.solex_process(opt, disk_list, bounds, hdr)
-            if to_host:
-                nbytes = 0
-                for im in results.values():
-                    nbytes += im.numpy().nbytes         # D2H into pinned memory
-                return nbytes
-        return 0
+        # every rank circularises / corrects the shifts whose images it owns (all of them at N=1)
+        Solex_recon.solex_process(opt, disk_list, bounds, hdr)
+        nbytes = 0
+        if to_host:
+            for im in results.values():
+                nbytes += im.numpy().nbytes             # D2H into pinned memory, through this rank's own PCIe link
+        return nbytes
 
     sampler = ClockSampler(local) if rank == 0 else None
 
@@ -305,6 +305,8 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             e2e['d2h'] = int(t.item())
         eng.pinned_free(host_ptr)
+    if world > 1:
+        parallel.release_exchange()
 
     # ---- roofline of the dominant kernel (pass-1 accumulation), timed live on its stream
     acc_ms = []
@@ -342,7 +344,8 @@ def run_b200(a):
         line = {
             'metric': METRIC, 'value': a.frames / (dev['ms_per_step'] * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dev['ms_per_step'], 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic', 'config': cfg,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic',
+            'config': dict(cfg, parallelism='frames sharded over %d rank(s); images owned by shift block' % world),
             'clocks': clocks, 'gpu_launches': dev['launches'],
             'stages_ms': {k: round(v, 3) for k, v in sorted(dev['stages'].items())},
             'roofline': {'bound': 'hbm', 'kernel': 'accumulate_u16_kernel (pass 1: integer sum + max of the stack)',

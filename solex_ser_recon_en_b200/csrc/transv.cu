@@ -258,16 +258,20 @@ __device__ __forceinline__ uint32_t ordered_key32(double x) {
     return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
+// Block-wide integer sum with ONE barrier: the per-warp partials alternate
+// between two halves of S.whist (parity = call counter), so a warp can only
+// overwrite a half after every thread has passed the barrier of the call in
+// between, i.e. after all reads of that half.
 template <int kT>
-__device__ __forceinline__ int block_sum_int(int v, Shared& S) {
+__device__ __forceinline__ int block_sum_int(int v, int parity, Shared& S) {
     constexpr int NW = kT / 32;
     v = __reduce_add_sync(0xffffffffu, v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) S.hist[threadIdx.x >> 5] = (unsigned int)v;
+    unsigned int* slot = &S.whist[parity & 1][0];
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = (unsigned int)v;
     __syncthreads();
     int t = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) t += (int)S.hist[w];
+    for (int w = 0; w < NW; ++w) t += (int)slot[w];
     return t;
 }
 
@@ -289,12 +293,13 @@ __device__ bool fast_select(const double* vals, int n, double med, int t, bool n
         }
     }
     transpose32(a);
+    __syncthreads();                                            // S.whist is free (earlier histogram users are done)
     bool split = false;
     uint32_t lo_set = 0, hi_set = 0;
 #pragma unroll
     for (int L = 0; L < 32; ++L) {
         const uint32_t slice = a[31 - L];
-        const int Z = block_sum_int<kT>(__popc(cand & ~slice), S);
+        const int Z = block_sum_int<kT>(__popc(cand & ~slice), L, S);
         if (need2 && t == Z - 1) {                             // rank t is the largest "0", rank t+1 the smallest "1"
             lo_set = cand & ~slice;
             hi_set = cand & slice;
@@ -452,10 +457,15 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // ---- mean of the inliers ---------------------------------------------------
     double sum = 0.0, cnt = 0.0;
     if (mdev != 0.0) {                               // (nan is truthy in the reference too, but cannot occur here)
+        // fl(d / mdev) < 2  <=>  d < 2*mdev for positive normal doubles (2*mdev is exact, and the largest
+        // double below it divides to at most 2 - 2^-52), so the per-element division is not needed
+        const double thr = 2.0 * mdev;
+        const bool exact = mdev > 1e-300 && mdev < 1e300;
         for (int i = threadIdx.x; i < n; i += kT) {
             const double r = vals[i];
-            const double s = fabs(r - med) / mdev;
-            if (s < 2.0) { sum += r; cnt += 1.0; }
+            const double d = fabs(r - med);
+            const bool keep = exact ? (d < thr) : (d / mdev < 2.0);
+            if (keep) { sum += r; cnt += 1.0; }
         }
     } else {
         for (int i = threadIdx.x; i < n; i += kT) { sum += vals[i]; cnt += 1.0; }

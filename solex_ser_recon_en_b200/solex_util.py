@@ -49,10 +49,14 @@ def _append(path, options, text, mode):
 
 
 def clearlog(path, options):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
     _append(path, options, 'start time: ' + str(datetime.datetime.now()) + '\n', 'w')
 
 
 def write_complete(path, options):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
     _append(path, options, 'end time: ' + str(datetime.datetime.now()) + '\n', 'a')
 
 
