@@ -22,7 +22,7 @@ import numpy as np
 from . import fits_min as fits
 from . import parallel, postprocess
 from .device_image import DeviceImage
-from .ellipse_to_circle import correct_image, ellipse_to_circle
+from .ellipse_to_circle import correct_image, ellipse_to_circle, fit_geometry
 from .solex_util import (clearlog, compute_mean_return_fit, correct_transversalium2, image_process, logme,
                          make_header, output_path, read_video_improved, write_complete)
 from .video_reader import video_reader
@@ -103,21 +103,28 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         geom = None
         if disk_list[0] is not None:
             basefich = basefich0 + '_shift=' + str(shifts[0])
-            circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+            plots = not options['clahe_only'] and not options['protus_only']
+            if plots and 0 in requested:
+                # diagnostic figure wanted: the one-image path draws it
+                circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+            else:
+                fit = fit_geometry(disk_list[0], options, basefich)
+                cercle0, ratio_fit, phi, borders = fit['circle'], fit['ratio'], fit['phi'], fit['borders']
             geom = (tuple(float(v) for v in cercle0), float(ratio_fit), float(phi), [float(b) for b in borders])
         cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_object(geom, src=0)
         options['slant_fix'] = math.degrees(phi)
-        todo = [i for i in requested if i != 0]
+        todo = [i for i in requested if i not in circular]
     else:
         todo = list(requested)
+        if todo and todo[0] == 0:                             # the reference logs the matrix for i == 0 only
+            circular[0] = correct_image(disk_list[0], math.radians(options['slant_fix'] or 0.0),
+                                        options['ratio_fixe'] if options['ratio_fixe'] is not None else 1.0,
+                                        np.array([-1.0, -1.0]), -1.0, options, print_log=True)[0]
+            todo = todo[1:]
     ratio = options['ratio_fixe'] if options['ratio_fixe'] is not None else 1.0
     phi = math.radians(options['slant_fix']) if options['slant_fix'] is not None else 0.0
-    # 2. circularise every other requested shift with that geometry (batched)
+    # 2. circularise every requested shift with that geometry: one min/max + one warp launch for the set
     if todo:
-        if todo[0] == 0:                                      # the reference logs the matrix for i == 0 only
-            circular[0] = correct_image(disk_list[0], phi, ratio, np.array([-1.0, -1.0]), -1.0, options,
-                                        print_log=True)[0]
-            todo = todo[1:]
         warped, _, _, _ = postprocess.circularise_many([disk_list[i] for i in todo], phi, ratio)
         circular.update(zip(todo, warped))
     # 3. transversalium for all requested shifts (batched), then the host tail per image

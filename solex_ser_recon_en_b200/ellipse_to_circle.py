@@ -37,6 +37,22 @@ def _as_frames(eng, image):
     return torch.from_numpy(dn).to(eng.device), False
 
 
+def _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height):
+    """The block correct_image prints / logs when print_log is set (reference :123-144)."""
+    basefich0 = options['basefich0']
+    log = basefich0 + '_log.txt'
+    print('unrotation angle theta = ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
+    np.set_printoptions(suppress=True)
+    logme(log, options, 'Y/X ratio : ' + '{:.3f}'.format(ratio))
+    print('Y/X ratio : ' + '{:.3f}'.format(ratio))
+    logme(log, options, 'Tilt angle : ' + '{:.3f}'.format(math.degrees(phi)) + ' degrees')
+    logme(log, options, 'Linear transform correction matrix : \n' + str(mat))
+    where = (str(new_center) + ', ' + '{:.3f}'.format(new_radius)) if not height == -1.0 else 'UNKNOWN'
+    logme(log, options, 'Disk position, radius : ' + where)
+    logme(log, options, 'Unrotation : ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
+    np.set_printoptions(suppress=False)
+
+
 def correct_image(image, phi, ratio, center, height, options, print_log=False):
     """Shear / scale the image along the scan axis so that the Sun is round
     (reference ellipse_to_circle.py:94-145).  Returns
@@ -52,20 +68,32 @@ def correct_image(image, phi, ratio, center, height, options, print_log=False):
         out = eng.warp_batch(frames, None, flip, mat3, out_shape, mm)[0]
     new_center, new_radius = geometry.moved_circle(np.asarray(center, dtype='d'), height, phi, ratio, (ih, n))
     if print_log:
-        basefich0 = options['basefich0']
-        log = basefich0 + '_log.txt'
-        print('unrotation angle theta = ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
-        np.set_printoptions(suppress=True)
-        logme(log, options, 'Y/X ratio : ' + '{:.3f}'.format(ratio))
-        print('Y/X ratio : ' + '{:.3f}'.format(ratio))
-        logme(log, options, 'Tilt angle : ' + '{:.3f}'.format(math.degrees(phi)) + ' degrees')
-        logme(log, options, 'Linear transform correction matrix : \n' + str(mat))
-        where = (str(new_center) + ', ' + '{:.3f}'.format(new_radius)) if not height == -1.0 else 'UNKNOWN'
-        logme(log, options, 'Disk position, radius : ' + where)
-        logme(log, options, 'Unrotation : ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
-        np.set_printoptions(suppress=False)
+        _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height)
     result = DeviceImage(eng, out) if isinstance(image, DeviceImage) else out.cpu().numpy()
     return result, (new_center[0], new_center[1], new_radius), mat3
+
+
+def fit_geometry(image, options, basefich=None):
+    """The fit half of ellipse_to_circle: limb search + ellipse fit + the geometry
+    of the correction, without warping anything.  Returns a dict with
+    phi, ratio, circle (cx, cy, radius after the warp), borders, mat3 and the
+    points used (for the diagnostic plot)."""
+    eng = get_engine()
+    frames, flip = _as_frames(eng, image)
+    n, ih = frames.shape
+    with eng.stage('ellipse_fit'):
+        sums = eng.downscale4(frames, flip)
+        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_device(eng, sums)
+    mat, mat3, _, _, theta = geometry.warp_plan((ih, n), phi, ratio)
+    new_center, new_radius = geometry.moved_circle(center, height, phi, ratio, (ih, n))
+    _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height)
+    pts = np.ones((kept.shape[0], 3))
+    pts[:, 0], pts[:, 1] = kept[:, 1], kept[:, 0]                             # (row, col) -> (x, y)
+    moved = (np.linalg.inv(mat3) @ pts.T).T
+    borders = [np.min(moved[:, 0]), np.min(moved[:, 1]), np.max(moved[:, 0]), np.max(moved[:, 1])]
+    print('sun borders found:' + str(borders))
+    return dict(phi=phi, ratio=ratio, circle=(new_center[0], new_center[1], new_radius), borders=borders, mat3=mat3,
+                center=center, height=height, kept=kept, raw=raw, outline=outline, frames=frames, flip=flip)
 
 
 def ellipse_to_circle(image, options, basefich):
@@ -73,22 +101,15 @@ def ellipse_to_circle(image, options, basefich):
     (reference ellipse_to_circle.py:294-342).
     Returns (image, (cx, cy, radius), ratio, phi, borders)."""
     eng = get_engine()
-    frames, flip = _as_frames(eng, image)
-    with eng.stage('ellipse_fit'):
-        sums = eng.downscale4(frames, flip)
-        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_device(eng, sums)
-    src = image if isinstance(image, DeviceImage) else DeviceImage(eng, frames, 'frames', flip)
-    fixed, circle, mat3 = correct_image(src, phi, ratio, center, height, options, print_log=True)
-    pts = np.ones((kept.shape[0], 3))
-    pts[:, 0], pts[:, 1] = kept[:, 1], kept[:, 0]                             # (row, col) -> (x, y)
-    moved = (np.linalg.inv(mat3) @ pts.T).T
-    borders = [np.min(moved[:, 0]), np.min(moved[:, 1]), np.max(moved[:, 0]), np.max(moved[:, 1])]
-    print('sun borders found:' + str(borders))
+    fit = fit_geometry(image, options, basefich)
+    src = image if isinstance(image, DeviceImage) else DeviceImage(eng, fit['frames'], 'frames', fit['flip'])
+    fixed, circle, mat3 = correct_image(src, fit['phi'], fit['ratio'], fit['center'], fit['height'], options)
     if not options['clahe_only'] and not options['protus_only']:
-        _plot_fit(image, fixed, raw, kept, outline, borders, output_path(basefich + '_ellipse_fit.png', options))
+        _plot_fit(image, fixed, fit['raw'], fit['kept'], fit['outline'], fit['borders'],
+                  output_path(basefich + '_ellipse_fit.png', options))
     if not isinstance(image, DeviceImage):
         fixed = np.asarray(fixed)
-    return fixed, circle, ratio, phi, borders
+    return fixed, circle, fit['ratio'], fit['phi'], fit['borders']
 
 
 def _plot_fit(image, fixed, raw, kept, outline, borders, path):
