@@ -237,29 +237,39 @@ extern "C" int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, voi
 
 extern "C" int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
                               uint32_t* h_out, uint32_t* d_work256, void* stream) {
-    SHG_REQUIRE(n > 0 && n_ranks >= 0, "shg_select_u32: empty input");
+    SHG_REQUIRE(n > 0 && n_ranks >= 0 && n_ranks <= 64, "shg_select_u32: empty input or too many ranks");
     cudaStream_t st = as_stream(stream);
     unsigned int hist[256];
-    for (int q = 0; q < n_ranks; ++q) {
-        int64_t rank = h_ranks[q];
-        SHG_REQUIRE(rank >= 0 && rank < n, "shg_select_u32: rank %lld out of range", (long long)rank);
-        uint32_t prefix = 0;
-        for (int shift = 24; shift >= 0; shift -= 8) {
+    std::vector<int64_t> rank(h_ranks, h_ranks + n_ranks);
+    std::vector<uint32_t> prefix(n_ranks, 0);
+    for (int q = 0; q < n_ranks; ++q)
+        SHG_REQUIRE(rank[q] >= 0 && rank[q] < n, "shg_select_u32: rank %lld out of range", (long long)rank[q]);
+    // MSB-first, one byte per pass; ranks that still share a prefix (the two middle elements of a
+    // median, the two neighbours of a percentile) share the histogram of that pass
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        std::vector<char> done(n_ranks, 0);
+        for (int q = 0; q < n_ranks; ++q) {
+            if (done[q]) continue;
             SHG_CHECK(cudaMemsetAsync(d_work256, 0, 256 * 4, st));
-            radix_hist_kernel<<<grid_for(n), 256, 0, st>>>(d_vals, n, prefix, shift, d_work256);
+            radix_hist_kernel<<<grid_for(n), 256, 0, st>>>(d_vals, n, prefix[q], shift, d_work256);
             SHG_LAUNCH_CHECK();
             SHG_CHECK(cudaMemcpyAsync(hist, d_work256, 256 * 4, cudaMemcpyDeviceToHost, st));
             SHG_CHECK(cudaStreamSynchronize(st));
-            int b = 0;
-            for (; b < 256; ++b) {
-                if (rank < (int64_t)hist[b]) break;
-                rank -= hist[b];
+            const uint32_t group = prefix[q];
+            for (int p = q; p < n_ranks; ++p) {
+                if (done[p] || prefix[p] != group) continue;
+                int b = 0;
+                for (; b < 256; ++b) {
+                    if (rank[p] < (int64_t)hist[b]) break;
+                    rank[p] -= hist[b];
+                }
+                SHG_REQUIRE(b < 256, "shg_select_u32: internal error (histogram does not cover the rank)");
+                prefix[p] = (group << 8) | (uint32_t)b;
+                done[p] = 1;
             }
-            SHG_REQUIRE(b < 256, "shg_select_u32: internal error (histogram does not cover the rank)");
-            prefix = (prefix << 8) | (uint32_t)b;
         }
-        h_out[q] = prefix;
     }
+    for (int q = 0; q < n_ranks; ++q) h_out[q] = prefix[q];
     return 0;
 }
 

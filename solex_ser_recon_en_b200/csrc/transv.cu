@@ -411,13 +411,30 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // ---- rat = log(img[y]/img[y-1]) -------------------------------------------
     double fmn = INFINITY, fmx = -INFINITY;
     unsigned int nnan = 0, nneg = 0, npos = 0;
-    for (int i = threadIdx.x; i < n; i += kT) {
-        const double r = logtab[ry[i]] - logtab[rp[i]];
-        vals[i] = r;
-        if (r != r) ++nnan;
-        else if (r == -INFINITY) ++nneg;
-        else if (r == INFINITY) ++npos;
-        else { fmn = fmin(fmn, r); fmx = fmax(fmx, r); }
+    // 8 independent pixel -> log-table chains in flight per thread (the loop is latency-bound otherwise)
+    for (int i0 = threadIdx.x; i0 < n; i0 += kT * 8) {
+        uint16_t pa[8], pb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kT;
+            pa[u] = i < n ? ry[i] : (uint16_t)1;
+            pb[u] = i < n ? rp[i] : (uint16_t)1;
+        }
+        double ta[8], tb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { ta[u] = logtab[pa[u]]; tb[u] = logtab[pb[u]]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kT;
+            if (i < n) {
+                const double r = ta[u] - tb[u];
+                vals[i] = r;
+                if (r != r) ++nnan;
+                else if (r == -INFINITY) ++nneg;
+                else if (r == INFINITY) ++npos;
+                else { fmn = fmin(fmn, r); fmx = fmax(fmx, r); }
+            }
+        }
     }
     if (threadIdx.x < 4) S.cnt[threadIdx.x] = 0;
     __syncthreads();

@@ -192,7 +192,7 @@ def two_step(points):
     center, width, height, phi = fit_ellipse(points)
     mat, _ = correction_matrix(phi, height / width)
     resid = np.linalg.norm(mat @ (points - np.array(center)).T * height, axis=0) - 1
-    kept = points[resid > -max(resid)]
+    kept = points[resid > -np.max(resid)]
     center, width, height, phi = fit_ellipse(kept)
     outline = ellipse_outline(center, width, height, phi)
     ratio = width / height
@@ -325,19 +325,25 @@ def limb_points_device(eng, sums, sigma=2.0):
             if len(flat_e):
                 break
         sigma -= 0.5
-    n_regions, lab = _components(flat_e, cols)
+    # labels of the surviving components, renumbered 1.. in raster order of their first pixel: what
+    # scipy.ndimage.label(edges) would give (a component survives hysteresis whole, so its pixels and
+    # the relative order of first pixels are unchanged)
+    kept_labels = np.flatnonzero(strong)
+    renum = np.zeros(count + 1, dtype=np.int64)
+    renum[kept_labels] = np.arange(1, len(kept_labels) + 1)
+    n_regions, lab = len(kept_labels), renum[lab[keep]]
     sizes = np.bincount(lab, minlength=n_regions + 1)
     sizes[0] = -1
     ranked = sorted(sizes.tolist(), reverse=True)[:min(n_regions, NUM_REG)]
     chosen = [sizes.tolist().index(s) for s in ranked]
     sel = np.isin(lab, chosen)
-    pts = np.stack([flat_e[sel] // cols, flat_e[sel] % cols], axis=1)
-    hull = set(map(tuple, pts[ConvexHull(pts).vertices]))
+    flat_sel = flat_e[sel]
+    pts = np.stack([flat_sel // cols, flat_sel % cols], axis=1)
+    hull_flat = flat_sel[ConvexHull(pts).vertices]
     kept = np.zeros(len(flat_e), bool)
     for c in chosen:
         region = lab == c
-        rp = np.stack([flat_e[region] // cols, flat_e[region] % cols], axis=1)
-        if any(tuple(p) in hull for p in rp):
+        if np.isin(flat_e[region], hull_flat).any():
             kept |= region
     lo, hi = pts[:, 0].min(), pts[:, 0].max()
     span = hi - lo

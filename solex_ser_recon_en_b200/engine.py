@@ -78,6 +78,32 @@ class DeviceStack:
         return a.view(np.uint8 if g.bytes_per_px == 1 else np.uint16).reshape(-1, g.height, g.width)
 
 
+def _bind_to_gpu_numa_node(index: int):
+    """Pin this process (one rank per GPU) to the CPUs NVML reports as local to
+    the GPU, so that pinned buffers are first-touched on the GPU's own NUMA node
+    and every rank's H2D stream stays on its own socket / PCIe root.  Returns
+    the CPU list, or None when NVML is unavailable or SHG_NO_AFFINITY is set."""
+    if os.environ.get('SHG_NO_AFFINITY') or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def _ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -113,6 +139,7 @@ class Engine:
         self.index = int(device)
         self.device = torch.device('cuda', self.index)
         torch.cuda.set_device(self.device)
+        self.cpu_affinity = _bind_to_gpu_numa_node(self.index)
         info = (C.c_int64 * 6)()
         call('shg_device_info', self.index, info)
         self.sm_count, self.cc = int(info[0]), (int(info[1]), int(info[2]))
