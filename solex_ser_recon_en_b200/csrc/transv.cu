@@ -239,16 +239,17 @@ __device__ void block_select(const double* vals, int n, double med, double lo, d
 // monotone, so keys strictly below the target key are strictly below in fp64;
 // the (usually single) elements that share the final key are ranked exactly in
 // fp64.  Ranks t and t+1 (even n) share the descent until they part ways.
-__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
-    // afterwards a[i] bit j == (old a[j]) bit i
-    uint32_t m = 0x0000FFFFu;
+// w[e] (e < 16) carries the 16-bit keys of elements e (low half) and e+16 (high
+// half); afterwards w[b] is the 32-element slice of key bit b (bit j = element j).
+__device__ __forceinline__ void transpose16x2(uint32_t (&w)[16]) {
+    uint32_t m = 0x00FF00FFu;
 #pragma unroll
-    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+    for (int j = 8; j != 0; j >>= 1, m ^= (m << j)) {
 #pragma unroll
-        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
-            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
-            a[k] ^= t << j;
-            a[k + j] ^= t;
+        for (int k = 0; k < 16; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((w[k] >> j) ^ w[k + j]) & m;
+            w[k] ^= t << j;
+            w[k + j] ^= t;
         }
     }
 }
@@ -276,53 +277,54 @@ __device__ __forceinline__ int block_sum_int(int v, int parity, Shared& S) {
 }
 
 // Returns true when handled (results in S.dbc[0..1]); false -> caller falls back to block_select.
+// Two rounds of 16 binary levels: the high half of the 32-bit key first (usually enough: the few
+// elements that share it are ranked exactly in fp64), the low half only when many elements tie.
 template <int KIND, int kT>
 __device__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
-    uint32_t a[32];
     uint32_t cand = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
         const int i = e * kT + (int)threadIdx.x;
-        a[e] = 0;
-        if (i < n) {
-            const double x = key_of<KIND>(vals, i, med);
-            if (fabs(x) < INFINITY) {                           // +-inf are ranked by the caller
-                a[e] = ordered_key32(x);
-                cand |= 1u << e;
+        if (i < n && fabs(key_of<KIND>(vals, i, med)) < INFINITY) cand |= 1u << e;   // +-inf are ranked by the caller
+    }
+    int m = block_sum_int<kT>(__popc(cand), 0, S);
+    int parity = 1;
+    for (int round = 0; round < 2 && m > kListCap / 2; ++round) {
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            uint32_t lo = 0, hi = 0;
+            const int i0 = e * kT + (int)threadIdx.x, i1 = (e + 16) * kT + (int)threadIdx.x;
+            if ((cand >> e) & 1u) lo = ordered_key32(key_of<KIND>(vals, i0, med));
+            if ((cand >> (e + 16)) & 1u) hi = ordered_key32(key_of<KIND>(vals, i1, med));
+            w[e] = round == 0 ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+        }
+        transpose16x2(w);
+#pragma unroll
+        for (int L = 0; L < 16; ++L) {
+            const uint32_t slice = w[15 - L];
+            const int Z = block_sum_int<kT>(__popc(cand & ~slice), parity++, S);
+            if (need2 && t == Z - 1) {                         // rank t is the largest "0", rank t+1 the smallest "1"
+                const uint32_t lo_set = cand & ~slice, hi_set = cand & slice;
+                double v0 = -INFINITY, v1 = INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int i = e * kT + (int)threadIdx.x;
+                    if ((lo_set >> e) & 1u) v0 = fmax(v0, key_of<KIND>(vals, i, med));
+                    if ((hi_set >> e) & 1u) v1 = fmin(v1, key_of<KIND>(vals, i, med));
+                }
+                block_minmax(v1, v0, S);
+                if (threadIdx.x == 0) { S.dbc[0] = v0; S.dbc[1] = v1; }
+                __syncthreads();
+                return true;
             }
+            if (t < Z) { cand &= ~slice; m = Z; }
+            else { t -= Z; cand &= slice; m -= Z; }
+            if (m <= 32) break;                                // few enough to rank directly
         }
     }
-    transpose32(a);
-    __syncthreads();                                            // S.whist is free (earlier histogram users are done)
-    bool split = false;
-    uint32_t lo_set = 0, hi_set = 0;
-#pragma unroll
-    for (int L = 0; L < 32; ++L) {
-        const uint32_t slice = a[31 - L];
-        const int Z = block_sum_int<kT>(__popc(cand & ~slice), L, S);
-        if (need2 && t == Z - 1) {                             // rank t is the largest "0", rank t+1 the smallest "1"
-            lo_set = cand & ~slice;
-            hi_set = cand & slice;
-            split = true;
-            break;
-        }
-        if (t < Z) cand &= ~slice;
-        else { t -= Z; cand &= slice; }
-    }
-    if (split) {
-        double v0 = -INFINITY, v1 = INFINITY;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int i = e * kT + (int)threadIdx.x;
-            if ((lo_set >> e) & 1u) v0 = fmax(v0, key_of<KIND>(vals, i, med));
-            if ((hi_set >> e) & 1u) v1 = fmin(v1, key_of<KIND>(vals, i, med));
-        }
-        block_minmax(v1, v0, S);
-        if (threadIdx.x == 0) { S.dbc[0] = v0; S.dbc[1] = v1; }
-        __syncthreads();
-        return true;
-    }
-    // every remaining candidate has the same 32-bit key: rank them exactly
+    // rank the remaining candidates exactly in fp64
+    __syncthreads();
     if (threadIdx.x == 0) S.list_n = 0;
     __syncthreads();
 #pragma unroll
@@ -333,12 +335,12 @@ __device__ bool fast_select(const double* vals, int n, double med, int t, bool n
         }
     }
     __syncthreads();
-    const int m = S.list_n;
-    if (m > kListCap) return false;                            // very many near-identical values: generic path
-    for (int c = threadIdx.x; c < m; c += kT) {
+    const int mm = S.list_n;
+    if (mm > kListCap) return false;                           // very many near-identical values: generic path
+    for (int c = threadIdx.x; c < mm; c += kT) {
         const double x = S.list[c];
         int rank = 0;
-        for (int i = 0; i < m; ++i) {
+        for (int i = 0; i < mm; ++i) {
             const double o = S.list[i];
             rank += (o < x || (o == x && i < c)) ? 1 : 0;
         }
