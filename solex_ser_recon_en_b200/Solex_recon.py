@@ -98,6 +98,12 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
     requested = [i for i in range(len(disk_list))
                  if shifts[i] in options['shift_requested'] and disk_list[i] is not None]
     circular = {}
+    # the min / max of the disks (the warp's clip range) only depends on the disks: start it now, on a
+    # side stream, so it runs underneath the ellipse fit
+    plots_wanted = not options['clahe_only'] and not options['protus_only']
+    early = [i for i in requested if not (i == 0 and (plots_wanted or options['ratio_fixe'] is not None
+                                                     or options['slant_fix'] is not None))]
+    prepared = postprocess.start_minmax([disk_list[i] for i in early])
     # 1. geometry: disk_list[0] is the ellipse-fit shift; the fit is made once (by its owner) and reused
     if options['ratio_fixe'] is None and options['slant_fix'] is None:
         geom = None
@@ -125,7 +131,8 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
     phi = math.radians(options['slant_fix']) if options['slant_fix'] is not None else 0.0
     # 2. circularise every requested shift with that geometry: one min/max + one warp launch for the set
     if todo:
-        warped, _, _, _ = postprocess.circularise_many([disk_list[i] for i in todo], phi, ratio)
+        warped, _, _, _ = postprocess.circularise_many([disk_list[i] for i in todo], phi, ratio,
+                                                       prepared if todo == early else None)
         circular.update(zip(todo, warped))
     # 3. transversalium for all requested shifts (batched), then the host tail per image
     images = [circular[i] for i in requested]

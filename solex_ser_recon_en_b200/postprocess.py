@@ -43,7 +43,33 @@ def _common_base(pairs):
     return base_ptr, idx, stride
 
 
-def circularise_many(images, phi, ratio):
+def start_minmax(images):
+    """Launch the per-image min / max of the disks on a side stream.  It depends
+    only on the disks, so solex_process starts it before the (host-heavy) ellipse
+    fit and the two overlap.  Returns a handle for circularise_many, or None."""
+    eng = get_engine()
+    if len(images) < 2 or not all(isinstance(im, DeviceImage) and im.layout == 'frames' for im in images):
+        return None
+    pairs = [(im.tensor, im.flip) for im in images]
+    common = _common_base(pairs)
+    if common is None:
+        return None
+    base_ptr, idx, stride = common
+    n, ih = pairs[0][0].shape
+    first = min(pairs, key=lambda p: p[0].data_ptr())[0]
+    base = torch.as_strided(first, (max(idx) + 1, n, ih), (stride, ih, 1))
+    if not hasattr(eng, '_side_stream'):
+        eng._side_stream = torch.cuda.Stream(device=eng.device)
+    side = eng._side_stream
+    side.wait_stream(torch.cuda.current_stream(eng.device))
+    with torch.cuda.stream(side):
+        mm = eng.minmax_device(base, idx)
+    done = torch.cuda.Event()
+    done.record(side)
+    return dict(ptrs=[p[0].data_ptr() for p in pairs], base=base, idx=idx, mm=mm, done=done)
+
+
+def circularise_many(images, phi, ratio, prepared=None):
     """Warp every image with the same (phi, ratio): one min/max launch and one
     warp launch for the whole set when the images are slices of one disk tensor
     (the normal case: read_video_improved's output).  Returns
@@ -61,8 +87,12 @@ def circularise_many(images, phi, ratio):
         span = max(idx) + 1
         # a (span, N, ih) view over the shared storage that starts at the lowest slice
         base = torch.as_strided(first, (span, n, ih), (stride, ih, 1))
-        with eng.stage('minmax'):
-            mm = eng.minmax_device(base, idx)
+        if prepared is not None and prepared['ptrs'] == [p[0].data_ptr() for p in pairs]:
+            torch.cuda.current_stream(eng.device).wait_event(prepared['done'])
+            mm = prepared['mm']
+        else:
+            with eng.stage('minmax'):
+                mm = eng.minmax_device(base, idx)
         with eng.stage('warp'):
             out = eng.warp_batch(base, idx, pairs[0][1], mat3, out_shape, mm)
         return [DeviceImage(eng, out[i]) for i in range(len(pairs))], mat, mat3, theta
