@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t qkey(double x, double lo, double scale) {
 // finite range [lo, hi]; m = number of such keys; 0 <= t (< t+1) < m.
 // Results in S.dbc[0], S.dbc[1].
 template <int KIND, int kT>
-__device__ void block_select(const double* vals, int n, double med, double lo, double hi, int m, int t, bool need2,
+__device__ __noinline__ void block_select(const double* vals, int n, double med, double lo, double hi, int m, int t, bool need2,
                              Shared& S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
@@ -280,7 +280,7 @@ __device__ __forceinline__ int block_sum_int(int v, int parity, Shared& S) {
 // Two rounds of 16 binary levels: the high half of the 32-bit key first (usually enough: the few
 // elements that share it are ranked exactly in fp64), the low half only when many elements tie.
 template <int KIND, int kT>
-__device__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
+__device__ __forceinline__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
     uint32_t cand = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
@@ -359,27 +359,25 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
                             int t0, int t1, double& v0, double& v1, Shared& S) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
-    const bool small = n <= 32 * kT;
-    auto select = [&](int t, bool need2) {
-        if (!(small && fast_select<KIND, kT>(vals, n, med, t, need2, S)))
-            block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t, need2, S);
-    };
     if (g0 == 0 && g1 == 0) {
-        select(t0 - nneg, t1 != t0);
+        // the common case: both middle ranks are finite values
+        if (!(n <= 32 * kT && fast_select<KIND, kT>(vals, n, med, t0 - nneg, t1 != t0, S)))
+            block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
         v0 = S.dbc[0];
         v1 = S.dbc[1];
         __syncthreads();
         return;
     }
+    // rows with so many zeros that a middle rank is +-inf: rare, generic path
     if (g0 == 0) {
-        select(t0 - nneg, false);
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, false, S);
         v0 = S.dbc[0];
         __syncthreads();
     } else {
         v0 = g0 < 0 ? -INFINITY : INFINITY;
     }
     if (g1 == 0) {
-        select(t1 - nneg, false);
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t1 - nneg, false, S);
         v1 = S.dbc[0];
         __syncthreads();
     } else {
@@ -388,7 +386,7 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
 }
 
 template <int kT>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, (kT == 128 ? 6 : 1))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
                         const int32_t* __restrict__ xb_list, int n_list,
