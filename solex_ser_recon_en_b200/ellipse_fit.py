@@ -315,7 +315,8 @@ def limb_points_device(eng, sums, sigma=2.0):
     while True:
         if sigma <= 0:
             raise Exception('ERROR: could not find any edges')
-        flat, mag = eng.canny_candidates(box, scale, level, gaussian_weights(sigma), low)
+        with eng.stage('ellipse_fit:canny(device)'):
+            flat, mag = eng.canny_candidates(box, scale, level, gaussian_weights(sigma), low)
         if len(flat):
             count, lab = _components(flat, cols)
             strong = np.zeros(count + 1, bool)
@@ -356,9 +357,11 @@ def limb_points_device(eng, sums, sigma=2.0):
 
 def fit_from_device(eng, sums):
     """fit_from_block_sums with the limb search on the GPU."""
-    pts, raw = limb_points_device(eng, sums)
+    with eng.stage('ellipse_fit:limb_search'):
+        pts, raw = limb_points_device(eng, sums)
     pts, raw = pts * 4, raw * 4
-    center, height, phi, ratio, kept, outline = two_step(pts)
+    with eng.stage('ellipse_fit:two_step(host)'):
+        center, height, phi, ratio, kept, outline = two_step(pts)
     return np.array([center[1], center[0]]), height, phi, ratio, kept, raw, outline
 
 
