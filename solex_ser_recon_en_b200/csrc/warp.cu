@@ -60,23 +60,35 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     const int nrow = min(r1, ih) - r0;                                // valid slit rows (may be <= 0)
     // ---- stage: coalesced along the slit axis (64 rows = 128 B per frame) ----
     const int n_stage = (int)(kend - kbase);
+    const bool interior = kbase >= 0 && kend <= n_frames && r1 <= ih && r1 - r0 == kRows;
     if (nrow == kRows && (ih & 7) == 0 && (((uintptr_t)disk) & 15) == 0) {
         // 16-byte loads: 8 lanes cover one frame's 64 rows, a warp takes 4 frames per instruction
         const int seg = threadIdx.x & 7;
-        for (int f = threadIdx.x >> 3; f < n_stage; f += 64) {          // two frames in flight per thread
-            const int f2 = f + 32;
-            const int64_t k0 = kbase + f, k1 = kbase + f2;
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-            const bool ok0 = k0 >= 0 && k0 < n_frames, ok1 = f2 < n_stage && k1 >= 0 && k1 < n_frames;
-            if (ok0) v0 = ld_stream_u4(reinterpret_cast<const uint4*>(disk + (flip ? (n_frames - 1 - k0) : k0) * ih + r0) + seg);
-            if (ok1) v1 = ld_stream_u4(reinterpret_cast<const uint4*>(disk + (flip ? (n_frames - 1 - k1) : k1) * ih + r0) + seg);
-            if (ok0) {
-                uint32_t* d = reinterpret_cast<uint32_t*>(tile + f * kPitch + seg * 8);
-                d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
+        const int64_t step = flip ? -(int64_t)ih : (int64_t)ih;
+        const uint16_t* src0 = disk + (flip ? (n_frames - 1 - kbase) : kbase) * (int64_t)ih + r0 + seg * 8;
+        if (interior) {
+            // every staged frame exists: two independent loads in flight per thread, no range tests
+            int f = threadIdx.x >> 3;
+            for (; f + 32 < n_stage; f += 64) {
+                const uint4 v0 = ld_stream_u4(reinterpret_cast<const uint4*>(src0 + f * step));
+                const uint4 v1 = ld_stream_u4(reinterpret_cast<const uint4*>(src0 + (f + 32) * step));
+                uint32_t* d0 = reinterpret_cast<uint32_t*>(tile + f * kPitch + seg * 8);
+                uint32_t* d1 = reinterpret_cast<uint32_t*>(tile + (f + 32) * kPitch + seg * 8);
+                d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w;
+                d1[0] = v1.x; d1[1] = v1.y; d1[2] = v1.z; d1[3] = v1.w;
             }
-            if (ok1) {
-                uint32_t* d = reinterpret_cast<uint32_t*>(tile + f2 * kPitch + seg * 8);
-                d[0] = v1.x; d[1] = v1.y; d[2] = v1.z; d[3] = v1.w;
+            if (f < n_stage) {
+                const uint4 v0 = ld_stream_u4(reinterpret_cast<const uint4*>(src0 + f * step));
+                uint32_t* d0 = reinterpret_cast<uint32_t*>(tile + f * kPitch + seg * 8);
+                d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w;
+            }
+        } else {
+            for (int f = threadIdx.x >> 3; f < n_stage; f += 32) {
+                const int64_t k = kbase + f;
+                if (k < 0 || k >= n_frames) continue;                      // never read (range test below)
+                const uint4 v0 = ld_stream_u4(reinterpret_cast<const uint4*>(src0 + f * step));
+                uint32_t* d0 = reinterpret_cast<uint32_t*>(tile + f * kPitch + seg * 8);
+                d0[0] = v0.x; d0[1] = v0.y; d0[2] = v0.z; d0[3] = v0.w;
             }
         }
     } else {
@@ -104,7 +116,32 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     const int ilo = (int)minmax[2 * img], ihi = (int)minmax[2 * img + 1];
     const int kb = (int)kbase, nf = (int)n_frames;
     constexpr double kMagic = 6755399441055744.0;                      // 1.5 * 2^52: x + kMagic holds floor(x) in its low word
-    for (int r = r0 + threadIdx.x / COLS; r < r1; r += RGROUPS) {
+    const int rg = threadIdx.x / COLS;
+    if (interior) {
+        // all taps of the tile are staged and valid: no range tests, no int -> double conversions in the loop
+        double rd = (double)(r0 + rg);
+        const uint16_t* col = tile + rg - kb * kPitch;
+        uint16_t* o = out + (int64_t)(r0 + rg) * out_cols + c;
+#pragma unroll 4
+        for (int r = r0 + rg; r < r1; r += RGROUPS) {
+            const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, rd)), m02);
+            const double xm = __dadd_rd(x, kMagic);
+            const int kf = __double2loint(xm);
+            const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));
+            const uint16_t* p = col + kf * kPitch;
+            const double L = u32_to_double(p[0]);
+            const double R = u32_to_double(p[d != 0.0 ? kPitch : 0]);
+            const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
+            int q = __double2loint(__dadd_rd(v, kMagic));
+            q = min(max(q, ilo), ihi);
+            *o = (uint16_t)q;
+            rd += (double)RGROUPS;
+            col += RGROUPS;
+            o += (int64_t)RGROUPS * out_cols;
+        }
+        return;
+    }
+    for (int r = r0 + rg; r < r1; r += RGROUPS) {
         const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
         const double xm = __dadd_rd(x, kMagic);
         const int kf = __double2loint(xm);                              // floor(x) (|x| < 2^31)
