@@ -142,8 +142,9 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
 
     const int tid = threadIdx.x;
     const int col = tid % TX, grp = tid / TX;
-    const int64_t n_tiles = n_frames * n_tx;
-    const int64_t first = blockIdx.x, stride = gridDim.x;
+    // a CTA keeps ONE column tile (tx) and walks frames: the per-column tables are read once
+    const int tx = blockIdx.x % n_tx;
+    const int64_t first = blockIdx.x / n_tx, stride = gridDim.x / n_tx;
     const uint32_t stage_bytes = (uint32_t)stage_elems * sizeof(T);
 
     uint64_t policy;
@@ -155,32 +156,28 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
     }
     __syncthreads();
 
-    auto issue = [&](int64_t tile, int stage) {
-        const int tx = (int)(tile % n_tx);
-        const int k = (int)(tile / n_tx);
+    auto issue = [&](int64_t k, int stage) {
         mbar_expect_tx(&full[stage], stage_bytes);
         T* dst = stage_buf + (size_t)stage * stage_elems;
         for (int r = 0; r < tab.n_runs; ++r)
-            tma_load_3d(dst + tab.run_off[r], &maps.m[r], &full[stage], tx * TX, row0[tx * tab.n_runs + r], k, policy);
+            tma_load_3d(dst + tab.run_off[r], &maps.m[r], &full[stage], tx * TX, row0[tx * tab.n_runs + r], (int)k, policy);
     };
 
     if (tid == 0)
         for (int s = 0; s < STAGES; ++s)
-            if (first + s * stride < n_tiles) issue(first + s * stride, s);
+            if (first + s * stride < n_frames) issue(first + s * stride, s);
 
     const int iw = H;
+    const int x = tx * TX + col;
+    const bool live = x < W;
+    const int i = W - 1 - x;
+    int f = 0;
+    double wl = 0.0, wr = 0.0;
+    if (live) { f = fl[i]; wl = lw[i]; wr = rw[i]; }
     int it = 0;
-    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+    for (int64_t k = first; k < n_frames; k += stride, ++it) {
         const int stage = it % STAGES;
         const uint32_t phase = (it / STAGES) & 1;
-        const int tx = (int)(tile % n_tx);
-        const int64_t k = tile / n_tx;
-        const int x = tx * TX + col;
-        const bool live = x < W;
-        const int i = W - 1 - x;
-        int f = 0;
-        double wl = 0.0, wr = 0.0;
-        if (live) { f = fl[i]; wl = lw[i]; wr = rw[i]; }
 
         mbar_wait(&full[stage], phase);
 
@@ -223,8 +220,8 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
         }
         __syncthreads();                                  // everyone is done with this stage
         if (tid == 0) {
-            const int64_t nxt = tile + (int64_t)STAGES * stride;
-            if (nxt < n_tiles) issue(nxt, stage);
+            const int64_t nxt = k + (int64_t)STAGES * stride;
+            if (nxt < n_frames) issue(nxt, stage);
         }
     }
 }
@@ -445,7 +442,10 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     const int by_smem = std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const int by_threads = std::max(1, 2048 / (TX * G));
     const int ctas_per_sm = std::min(by_smem, by_threads);
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * ctas_per_sm);
+    // grid = n_tx column tiles x frame lanes (a multiple of n_tx, close to one full wave of resident CTAs)
+    const int64_t lanes = std::max<int64_t>(1, std::min<int64_t>(n_frames, ((int64_t)sms * ctas_per_sm) / plan.n_tx));
+    const unsigned grid = (unsigned)(lanes * plan.n_tx);
+    (void)n_tiles;
 
 #define SHG_LAUNCH_TMA(T, TXV, ST, GV)                                                                     \
     do {                                                                                                   \
