@@ -329,14 +329,15 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     const int64_t row_bytes = (int64_t)W * bytes_per_px;
     bool tma = rot && impl != 1 && row_bytes % 16 == 0 && ((int64_t)H * row_bytes) % 16 == 0 &&
                ((uintptr_t)d_frames % 16 == 0) && n_frames < (1LL << 31);
-    int TX = 0, stages = 0, G = 4;
+    int TX = 0, stages = 0, G = 2;
     if (tma) {
-        // tile width / shift groups: TX*G threads per CTA.  Default 128 columns x 4 groups
-        // (two CTAs per SM with 4 stages at config-5 band heights); SHG_RECON_TX / _G override for tuning.
-        int want_tx = 128;
+        // tile width / shift groups: TX*G threads per CTA.  Default 256 columns x 2 groups (one 512-thread CTA
+        // per SM with 3 stages at config-5 band heights: 5.5 ms vs 5.9 ms for 128 x 4 on a B200);
+        // SHG_RECON_TX / _G override for tuning.
+        int want_tx = 256;
         if (const char* e = getenv("SHG_RECON_TX")) want_tx = atoi(e);
         if (const char* e = getenv("SHG_RECON_G")) G = atoi(e);
-        if (G != 1 && G != 2 && G != 4 && G != 8) G = 4;
+        if (G != 1 && G != 2 && G != 4 && G != 8) G = 2;
         int cands[3] = {want_tx, 128, 64};
         for (int cand : cands) {
             if (cand != 64 && cand != 128 && cand != 256) continue;

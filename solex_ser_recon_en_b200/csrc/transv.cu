@@ -12,6 +12,8 @@
 // good to ~1e-16 relative of a value that is ~1e-2).
 // Stage 2 (shg_row_scale_u16): out = trunc(min(img * gain[row], 65535)).
 // Bound: HBM (each image is read once per stage, written once by stage 2).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -386,7 +388,7 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
 }
 
 template <int kT>
-__global__ void __launch_bounds__(kT, (kT == 128 ? 6 : 1))
+__global__ void __launch_bounds__(kT, (kT == 128 ? 6 : (kT == 256 ? 3 : 1)))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
                         const int32_t* __restrict__ xb_list, int n_list,
@@ -663,8 +665,13 @@ extern "C" int shg_log_table(double* d_tab65536, void* stream) {
 }
 
 static int transv_threads(int max_len) {
-    // enough threads that each owns <= ~32 elements, few enough that several rows share an SM
-    return max_len <= 4096 ? 128 : (max_len <= 16384 ? 512 : 1024);
+    // enough threads that each owns <= 32 elements (the bit-sliced select), few enough that several rows share an SM
+    int t = max_len <= 4096 ? 128 : (max_len <= 8192 ? 256 : (max_len <= 16384 ? 512 : 1024));
+    if (const char* e = getenv("SHG_TRANSV_T")) {            // tuning knob
+        const int v = atoi(e);
+        if ((v == 128 || v == 256 || v == 512 || v == 1024) && max_len <= 32 * v) t = v;
+    }
+    return t;
 }
 
 static int64_t transv_smem_cap(int optin) {
@@ -715,6 +722,7 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     } while (0)
     const int threads = transv_threads(max_len);
     if (threads == 128) SHG_TRANSV_LAUNCH(128);
+    else if (threads == 256) SHG_TRANSV_LAUNCH(256);
     else if (threads == 512) SHG_TRANSV_LAUNCH(512);
     else SHG_TRANSV_LAUNCH(1024);
     SHG_LAUNCH_CHECK();
