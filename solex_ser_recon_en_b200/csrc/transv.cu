@@ -281,47 +281,70 @@ __device__ __forceinline__ int block_sum_int(int v, int parity, Shared& S) {
 // Returns true when handled (results in S.dbc[0..1]); false -> caller falls back to block_select.
 // Two rounds of 16 binary levels: the high half of the 32-bit key first (usually enough: the few
 // elements that share it are ranked exactly in fp64), the low half only when many elements tie.
-template <int KIND, int kT>
+// A thread owns up to 32*WORDS elements (element e of word q is vals[(32q + e)*kT + tid]).
+template <int KIND, int kT, int WORDS>
 __device__ __forceinline__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
-    uint32_t cand = 0;
+    uint32_t cand[WORDS];
+    int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        const int i = e * kT + (int)threadIdx.x;
-        if (i < n && fabs(key_of<KIND>(vals, i, med)) < INFINITY) cand |= 1u << e;   // +-inf are ranked by the caller
+    for (int q = 0; q < WORDS; ++q) {
+        cand[q] = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int i = (32 * q + e) * kT + (int)threadIdx.x;
+            if (i < n && fabs(key_of<KIND>(vals, i, med)) < INFINITY) cand[q] |= 1u << e;   // +-inf: ranked by the caller
+        }
+        cnt += __popc(cand[q]);
     }
-    int m = block_sum_int<kT>(__popc(cand), 0, S);
+    int m = block_sum_int<kT>(cnt, 0, S);
     int parity = 1;
     for (int round = 0; round < 2 && m > kListCap / 2; ++round) {
-        uint32_t w[16];
+        uint32_t w[WORDS][16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            uint32_t lo = 0, hi = 0;
-            const int i0 = e * kT + (int)threadIdx.x, i1 = (e + 16) * kT + (int)threadIdx.x;
-            if ((cand >> e) & 1u) lo = ordered_key32(key_of<KIND>(vals, i0, med));
-            if ((cand >> (e + 16)) & 1u) hi = ordered_key32(key_of<KIND>(vals, i1, med));
-            w[e] = round == 0 ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+        for (int q = 0; q < WORDS; ++q) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                uint32_t lo = 0, hi = 0;
+                const int i0 = (32 * q + e) * kT + (int)threadIdx.x, i1 = (32 * q + e + 16) * kT + (int)threadIdx.x;
+                if ((cand[q] >> e) & 1u) lo = ordered_key32(key_of<KIND>(vals, i0, med));
+                if ((cand[q] >> (e + 16)) & 1u) hi = ordered_key32(key_of<KIND>(vals, i1, med));
+                w[q][e] = round == 0 ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+            }
+            transpose16x2(w[q]);
         }
-        transpose16x2(w);
 #pragma unroll
         for (int L = 0; L < 16; ++L) {
-            const uint32_t slice = w[15 - L];
-            const int Z = block_sum_int<kT>(__popc(cand & ~slice), parity++, S);
+            int z = 0;
+#pragma unroll
+            for (int q = 0; q < WORDS; ++q) z += __popc(cand[q] & ~w[q][15 - L]);
+            const int Z = block_sum_int<kT>(z, parity++, S);
             if (need2 && t == Z - 1) {                         // rank t is the largest "0", rank t+1 the smallest "1"
-                const uint32_t lo_set = cand & ~slice, hi_set = cand & slice;
                 double v0 = -INFINITY, v1 = INFINITY;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int i = e * kT + (int)threadIdx.x;
-                    if ((lo_set >> e) & 1u) v0 = fmax(v0, key_of<KIND>(vals, i, med));
-                    if ((hi_set >> e) & 1u) v1 = fmin(v1, key_of<KIND>(vals, i, med));
+                for (int q = 0; q < WORDS; ++q) {
+                    const uint32_t lo_set = cand[q] & ~w[q][15 - L], hi_set = cand[q] & w[q][15 - L];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int i = (32 * q + e) * kT + (int)threadIdx.x;
+                        if ((lo_set >> e) & 1u) v0 = fmax(v0, key_of<KIND>(vals, i, med));
+                        if ((hi_set >> e) & 1u) v1 = fmin(v1, key_of<KIND>(vals, i, med));
+                    }
                 }
                 block_minmax(v1, v0, S);
                 if (threadIdx.x == 0) { S.dbc[0] = v0; S.dbc[1] = v1; }
                 __syncthreads();
                 return true;
             }
-            if (t < Z) { cand &= ~slice; m = Z; }
-            else { t -= Z; cand &= slice; m -= Z; }
+            if (t < Z) {
+#pragma unroll
+                for (int q = 0; q < WORDS; ++q) cand[q] &= ~w[q][15 - L];
+                m = Z;
+            } else {
+                t -= Z;
+#pragma unroll
+                for (int q = 0; q < WORDS; ++q) cand[q] &= w[q][15 - L];
+                m -= Z;
+            }
             if (m <= 32) break;                                // few enough to rank directly
         }
     }
@@ -330,10 +353,13 @@ __device__ __forceinline__ bool fast_select(const double* vals, int n, double me
     if (threadIdx.x == 0) S.list_n = 0;
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        if ((cand >> e) & 1u) {
-            const int slot = atomicAdd(&S.list_n, 1);
-            if (slot < kListCap) S.list[slot] = key_of<KIND>(vals, e * kT + (int)threadIdx.x, med);
+    for (int q = 0; q < WORDS; ++q) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            if ((cand[q] >> e) & 1u) {
+                const int slot = atomicAdd(&S.list_n, 1);
+                if (slot < kListCap) S.list[slot] = key_of<KIND>(vals, (32 * q + e) * kT + (int)threadIdx.x, med);
+            }
         }
     }
     __syncthreads();
@@ -363,7 +389,8 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
     const int g0 = group(t0), g1 = group(t1);
     if (g0 == 0 && g1 == 0) {
         // the common case: both middle ranks are finite values
-        if (!(n <= 32 * kT && fast_select<KIND, kT>(vals, n, med, t0 - nneg, t1 != t0, S)))
+        constexpr int kWords = kT <= 64 ? 2 : 1;              // 64-thread CTAs own up to 64 elements per thread
+        if (!(n <= 32 * kWords * kT && fast_select<KIND, kT, kWords>(vals, n, med, t0 - nneg, t1 != t0, S)))
             block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
         v0 = S.dbc[0];
         v1 = S.dbc[1];
@@ -388,7 +415,7 @@ __device__ void ranked_pair(const double* vals, int n, double med, double lo, do
 }
 
 template <int kT>
-__global__ void __launch_bounds__(kT, (kT == 128 ? 6 : (kT == 256 ? 3 : 1)))
+__global__ void __launch_bounds__(kT, (kT == 64 ? 6 : (kT == 128 ? 6 : (kT == 256 ? 3 : 1))))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
                         const int32_t* __restrict__ xb_list, int n_list,
@@ -669,6 +696,7 @@ static int transv_threads(int max_len) {
     int t = max_len <= 4096 ? 128 : (max_len <= 8192 ? 256 : (max_len <= 16384 ? 512 : 1024));
     if (const char* e = getenv("SHG_TRANSV_T")) {            // tuning knob
         const int v = atoi(e);
+        if (v == 64 && max_len <= 4096) t = 64;
         if ((v == 128 || v == 256 || v == 512 || v == 1024) && max_len <= 32 * v) t = v;
     }
     return t;
@@ -721,7 +749,8 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
                                                           smem_cap);                                                \
     } while (0)
     const int threads = transv_threads(max_len);
-    if (threads == 128) SHG_TRANSV_LAUNCH(128);
+    if (threads == 64) SHG_TRANSV_LAUNCH(64);
+    else if (threads == 128) SHG_TRANSV_LAUNCH(128);
     else if (threads == 256) SHG_TRANSV_LAUNCH(256);
     else if (threads == 512) SHG_TRANSV_LAUNCH(512);
     else SHG_TRANSV_LAUNCH(1024);

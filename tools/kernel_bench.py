@@ -53,6 +53,30 @@ def main():
         return only is None or k in only
 
     stack_bytes = a.frames * geom.frame_bytes
+    if only is not None and 'ingest' in only:
+        # file -> pinned ring -> HBM (+ overlapped pass 1) from a tmpfs SER file of min(frames, 2000) frames
+        import time
+        from solex_ser_recon_en_b200 import synth
+        nf = min(a.frames, 2000)
+        g2 = ScanGeometry(a.width, a.height, a.bpp, nf)
+        path = '/dev/shm/shg_ingest_bench.SER'
+        host = st.frames[:nf * geom.frame_bytes].cpu().numpy()
+        with open(path, 'wb') as f:
+            f.write(synth.ser_header(a.width, a.height, 8 * a.bpp, nf))
+            f.write(host.tobytes())
+        del host
+        for threads, slot_mb, slots in ((1, 64, 4), (4, 64, 4), (8, 64, 4), (16, 64, 4), (8, 256, 4), (16, 256, 6)):
+            best = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter()
+                s2, stats = eng.ingest_file(path, g2, 178, n_threads=threads, slot_mb=slot_mb, n_slots=slots)
+                best = min(best, time.perf_counter() - t0)
+                del s2
+            res['ingest_file t=%d slot=%dMB x%d' % (threads, slot_mb, slots)] = dict(
+                ms=best * 1e3, GBps=nf * geom.frame_bytes / best / 1e9, read_wait_ms=stats[1] * 1e3)
+        os.remove(path)
+        print(json.dumps(dict(config=vars(a), results=res), indent=1))
+        return
     if want('accumulate'):
         ms, best = timed(lambda: eng.accumulate(st), a.reps)
         res['accumulate'] = dict(ms=ms, best_ms=best, GBps=stack_bytes / ms / 1e6)
