@@ -30,15 +30,27 @@ from .video_reader import video_reader
 
 def solex_do_work(tasks, flag_command_line=False):
     """Process a list of (file, options) tasks; returns None, raises on the first bad file
-    like the reference (the caller's try/except reports it)."""
-    with ThreadPoolExecutor(max_workers=4) as pool:
-        pending = []
+    like the reference (the caller's try/except reports it).
+
+    The reference overlaps "read file i+1" with "post-process file i" through a process pool
+    (Solex_recon.py:30-42).  Here file i+1 is ingested (pinned ring -> H2D on the ingest streams,
+    the call releases the GIL) while one worker thread runs the GPU post-processing of file i and
+    four more run the host tails (CLAHE + PNG / FITS)."""
+    with ThreadPoolExecutor(max_workers=1) as gpu_post, ThreadPoolExecutor(max_workers=4) as tails:
+        posts = []
         for file, options in tasks:
             print('file %s is processing' % file)
             disk_list, backup_bounds, hdr = solex_read(file, options)
-            pending += solex_process(options, disk_list, backup_bounds, hdr, _pool=pool)
-        for fut in pending:
-            fut.result()
+            if parallel.world()[1] > 1:
+                # collectives must be issued in the same order on every rank: no second thread
+                for fut in solex_process(options, disk_list, backup_bounds, hdr, tails):
+                    fut.result()
+            else:
+                posts.append(gpu_post.submit(solex_process, options, disk_list, backup_bounds, hdr, tails))
+            del disk_list
+        for post in posts:
+            for fut in post.result():
+                fut.result()
 
 
 def solex_read(file, options):
