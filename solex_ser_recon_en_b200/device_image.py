@@ -26,6 +26,7 @@ class DeviceImage:
         self.engine, self.tensor, self.layout, self.flip = engine, tensor, layout, bool(flip)
         self._host = None
         self._rows = None
+        self.fit_future = None        # limb search started early on this image (solex_util.read_video_improved)
 
     # ---- array protocol -----------------------------------------------------
     @property
@@ -73,7 +74,9 @@ class DeviceImage:
     def flipped(self):
         """np.flip(self, axis=1) without touching the pixels."""
         if self.layout == 'frames':
-            return DeviceImage(self.engine, self.tensor, 'frames', not self.flip)
+            out = DeviceImage(self.engine, self.tensor, 'frames', not self.flip)
+            out.fit_future = self.fit_future      # the early fit was started on the image as it will be used
+            return out
         return np.flip(self.numpy(), axis=1)
 
     def __getattr__(self, name):

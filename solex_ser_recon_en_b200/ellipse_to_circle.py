@@ -73,6 +73,39 @@ def correct_image(image, phi, ratio, center, height, options, print_log=False):
     return result, (new_center[0], new_center[1], new_radius), mat3
 
 
+def _fit_points(eng, frames, flip):
+    with eng.stage('ellipse_fit'):
+        sums = eng.downscale4(frames, flip)
+        return ellipse_fit.fit_from_device(eng, sums)
+
+
+_fit_pool = None
+
+
+def start_fit(image):
+    """Start the limb search + ellipse fit of a frame-major DeviceImage in a helper
+    thread, on a side stream that first waits for everything already queued on
+    the current stream (the kernel that produced the image).  Returns a future of
+    _fit_points' result; fit_geometry picks it up through image.fit_future."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    global _fit_pool
+    eng = get_engine()
+    if _fit_pool is None:
+        _fit_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='shg-fit')
+    if not hasattr(eng, '_fit_stream'):
+        eng._fit_stream = torch.cuda.Stream(device=eng.device)
+    side = eng._fit_stream
+    side.wait_stream(torch.cuda.current_stream(eng.device))
+    frames, flip = image.tensor, image.flip
+
+    def job():
+        torch.cuda.set_device(eng.device)
+        with torch.cuda.stream(side):
+            return _fit_points(eng, frames, flip)
+    return _fit_pool.submit(job)
+
+
 def fit_geometry(image, options, basefich=None):
     """The fit half of ellipse_to_circle: limb search + ellipse fit + the geometry
     of the correction, without warping anything.  Returns a dict with
@@ -81,9 +114,12 @@ def fit_geometry(image, options, basefich=None):
     eng = get_engine()
     frames, flip = _as_frames(eng, image)
     n, ih = frames.shape
-    with eng.stage('ellipse_fit'):
-        sums = eng.downscale4(frames, flip)
-        center, height, phi, ratio, kept, raw, outline = ellipse_fit.fit_from_device(eng, sums)
+    early = getattr(image, 'fit_future', None)
+    if early is not None:
+        image.fit_future = None
+        center, height, phi, ratio, kept, raw, outline = early.result()      # started under the reconstruction
+    else:
+        center, height, phi, ratio, kept, raw, outline = _fit_points(eng, frames, flip)
     mat, mat3, _, _, theta = geometry.warp_plan((ih, n), phi, ratio)
     new_center, new_radius = geometry.moved_circle(center, height, phi, ratio, (ih, n))
     _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height)

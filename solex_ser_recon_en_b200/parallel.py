@@ -176,23 +176,44 @@ def gather_rows(local_disk, n_frames: int, dst: int = 0):
     return None
 
 
-def reconstruct(stack, fit: np.ndarray, shifts):
+def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     """Reconstruct this rank's frames at every shift.  Returns a list with one
     frame-major (N, ih) device image per shift -- every image on a single GPU;
-    with several ranks, the images this rank owns and None for the others."""
+    with several ranks, the images this rank owns and None for the others.
+
+    `first_done(image0)` (optional) is called as soon as the image of shifts[0]
+    -- the ellipse-fit shift -- is complete (on its owner, rank 0), while the
+    other shifts are still being reconstructed: the caller starts the limb
+    search there so that its host-side part hides under the big kernel."""
     eng = get_engine()
     rank, size = world()
+    n_s = len(shifts)
+    split = first_done is not None and n_s > 1
     if size == 1:
-        local = eng.recon(stack, fit, shifts)
-        return [local[i] for i in range(len(shifts))]
+        disk = eng.alloc_disk(n_s, stack.n, stack.geom.ih)
+        if split:
+            eng.recon(stack, fit, shifts[:1], disk=disk[:1], k0_out=0)
+            first_done(disk[0])
+            eng.recon(stack, fit, shifts[1:], disk=disk[1:], k0_out=0)
+        else:
+            eng.recon(stack, fit, shifts, disk=disk, k0_out=0)
+        return [disk[i] for i in range(n_s)]
     g = stack.geom
-    ex = row_exchange(len(shifts), g.n_frames, g.ih)
+    ex = row_exchange(n_s, g.n_frames, g.ih)
     torch.cuda.synchronize()
     dist.barrier()                         # owners are done reading the previous scan's images
-    eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0)
+    if split:
+        eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0)
+        torch.cuda.synchronize()
+        dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
+        if ex.owner[0] == rank:
+            first_done(ex.images[0])
+        eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0)
+    else:
+        eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0)
     torch.cuda.synchronize()
     dist.barrier()                         # every rank's rows have landed
-    out = [None] * len(shifts)
+    out = [None] * n_s
     for n, j in enumerate(ex.mine):
         out[j] = ex.images[n]
     return out

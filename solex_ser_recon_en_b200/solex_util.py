@@ -259,10 +259,22 @@ def read_video_improved(rdr, fit, options):
     stack = resident_stack(rdr, accumulate=False)
     shifts = [int(s) for s in options['shift']]
     from . import parallel
+    # When an ellipse fit will follow (Solex_recon.solex_process, no fixed ratio / tilt), the image of the
+    # ellipse-fit shift is reconstructed first and the limb search starts on it in a helper thread and on
+    # a side stream, underneath the reconstruction of the other shifts.
+    prefetch = {}
+    first_done = None
+    wants_fit = options.get('_prefetch_fit') and options.get('ratio_fixe') is None and options.get('slant_fix') is None
+    if wants_fit:
+        def first_done(image0):
+            from .ellipse_to_circle import start_fit
+            prefetch['fit'] = start_fit(DeviceImage(eng, image0, 'frames', bool(options.get('flip_x'))))
     with eng.stage('recon+gather'):
-        disk = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts)
+        disk = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
     # one image per shift; under several ranks only the images this rank owns (None elsewhere)
     disk_list = [None if d is None else DeviceImage(eng, d, 'frames') for d in disk]
+    if 'fit' in prefetch and disk_list[0] is not None:
+        disk_list[0].fit_future = prefetch['fit']
     if options['flag_display'] and disk_list[1] is not None:
         cv2.namedWindow('disk', cv2.WINDOW_NORMAL)
         cv2.imshow('disk', np.asarray(disk_list[1]))             # disk_list[1] is always shift = 0
