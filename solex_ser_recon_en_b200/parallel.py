@@ -192,7 +192,8 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     if size == 1:
         disk = eng.alloc_disk(n_s, stack.n, stack.geom.ih)
         if split:
-            eng.recon(stack, fit, shifts[:1], disk=disk[:1], k0_out=0)
+            # one shift = two band rows per frame: the direct-load kernel (impl 1) beats a TMA tile that small
+            eng.recon(stack, fit, shifts[:1], disk=disk[:1], k0_out=0, impl=1)
             first_done(disk[0])
             eng.recon(stack, fit, shifts[1:], disk=disk[1:], k0_out=0)
         else:
@@ -203,7 +204,7 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     torch.cuda.synchronize()
     dist.barrier()                         # owners are done reading the previous scan's images
     if split:
-        eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0)
+        eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0, impl=1)
         torch.cuda.synchronize()
         dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
         if ex.owner[0] == rank:
