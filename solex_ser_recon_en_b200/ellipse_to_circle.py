@@ -82,10 +82,10 @@ def _fit_points(eng, frames, flip):
 _fit_pool = None
 
 
-def start_fit(image):
+def start_fit(image, ready=None):
     """Start the limb search + ellipse fit of a frame-major DeviceImage in a helper
-    thread, on a side stream that first waits for everything already queued on
-    the current stream (the kernel that produced the image).  Returns a future of
+    thread, on a side stream that first waits for the kernel that produced the
+    image (`ready`, or everything queued on the current stream).  Returns a future of
     _fit_points' result; fit_geometry picks it up through image.fit_future."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
@@ -96,7 +96,10 @@ def start_fit(image):
     if not hasattr(eng, '_fit_stream'):
         eng._fit_stream = torch.cuda.Stream(device=eng.device)
     side = eng._fit_stream
-    side.wait_stream(torch.cuda.current_stream(eng.device))
+    if ready is not None:
+        side.wait_event(ready)                  # only the kernel that produced this image, not what was queued after it
+    else:
+        side.wait_stream(torch.cuda.current_stream(eng.device))
     frames, flip = image.tensor, image.flip
 
     def job():

@@ -181,7 +181,7 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     frame-major (N, ih) device image per shift -- every image on a single GPU;
     with several ranks, the images this rank owns and None for the others.
 
-    `first_done(image0)` (optional) is called as soon as the image of shifts[0]
+    `first_done(image0, ready_event)` (optional) is called once the image of shifts[0]
     -- the ellipse-fit shift -- is complete (on its owner, rank 0), while the
     other shifts are still being reconstructed: the caller starts the limb
     search there so that its host-side part hides under the big kernel."""
@@ -194,8 +194,12 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
         if split:
             # one shift = two band rows per frame: the direct-load kernel (impl 1) beats a TMA tile that small
             eng.recon(stack, fit, shifts[:1], disk=disk[:1], k0_out=0, impl=1)
-            first_done(disk[0])
+            ready = torch.cuda.Event()
+            ready.record()
+            # queue the big kernel BEFORE waking the helper thread: the helper's Python work would otherwise
+            # hold the interpreter lock while this thread still has the launch to do
             eng.recon(stack, fit, shifts[1:], disk=disk[1:], k0_out=0)
+            first_done(disk[0], ready)
         else:
             eng.recon(stack, fit, shifts, disk=disk, k0_out=0)
         return [disk[i] for i in range(n_s)]
@@ -207,9 +211,9 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
         eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0, impl=1)
         torch.cuda.synchronize()
         dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
-        if ex.owner[0] == rank:
-            first_done(ex.images[0])
         eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0)
+        if ex.owner[0] == rank:
+            first_done(ex.images[0], None)             # image 0 is complete (barrier above)
     else:
         eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0)
     torch.cuda.synchronize()

@@ -266,9 +266,9 @@ def read_video_improved(rdr, fit, options):
     first_done = None
     wants_fit = options.get('_prefetch_fit') and options.get('ratio_fixe') is None and options.get('slant_fix') is None
     if wants_fit:
-        def first_done(image0):
+        def first_done(image0, ready):
             from .ellipse_to_circle import start_fit
-            prefetch['fit'] = start_fit(DeviceImage(eng, image0, 'frames', bool(options.get('flip_x'))))
+            prefetch['fit'] = start_fit(DeviceImage(eng, image0, 'frames', bool(options.get('flip_x'))), ready)
     with eng.stage('recon+gather'):
         disk = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
     # one image per shift; under several ranks only the images this rank owns (None elsewhere)
