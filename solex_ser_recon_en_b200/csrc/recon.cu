@@ -38,6 +38,7 @@ struct ShiftTable {
     int run_unit[kMaxRuns];        // 1 when the run's shifts are consecutive integers
     short sh[kMaxShifts];
     short slot[kMaxShifts];        // output image index of sh[j]
+    short seg_end[kMaxShifts];     // end (exclusive) of the maximal run of consecutive integers that contains sh[j]
 };
 
 struct TmaMaps {
@@ -191,19 +192,23 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
                 const int per = (jb - ja + G - 1) / G;
                 const int j0 = ja + grp * per, j1 = min(jb, j0 + per);
                 if (j0 >= j1) continue;
-                const int first_il = f + tab.sh[j0];
-                if (tab.run_unit[r] && first_il >= 0 && first_il + (j1 - 1 - j0) <= iw - 2) {
-                    // consecutive shifts, nothing clipped: walk down the band one row per shift;
-                    // each tap is loaded and converted once (right tap of shift s = left tap of s+1)
-                    const T* p = rb + (first_il - base) * TX;
-                    double Lw = __dmul_rn(px_to_double<T>(p[0]), wl);
+                if (f + tab.sh[j0] >= 0 && f + tab.sh[j1 - 1] <= iw - 2) {
+                    // nothing clipped: walk down the band one row per shift through each stretch of
+                    // consecutive shifts; every tap is loaded and converted once (right tap of shift s =
+                    // left tap of s+1)
+                    int j = j0;
+                    while (j < j1) {
+                        const int je = min(j1, (int)tab.seg_end[j]);
+                        const T* p = rb + (f + tab.sh[j] - base) * TX;
+                        double Lw = __dmul_rn(px_to_double<T>(p[0]), wl);
 #pragma unroll 4
-                    for (int j = j0; j < j1; ++j) {
-                        p += TX;
-                        const double R = px_to_double<T>(p[0]);
-                        const double v = __dadd_rn(Lw, __dmul_rn(R, wr));
-                        Lw = __dmul_rn(R, wl);
-                        st_global_u16(s_out[j] + off2, (uint16_t)double_floor_to_u32(v));
+                        for (; j < je; ++j) {
+                            p += TX;
+                            const double R = px_to_double<T>(p[0]);
+                            const double v = __dadd_rn(Lw, __dmul_rn(R, wr));
+                            Lw = __dmul_rn(R, wl);
+                            st_global_u16(s_out[j] + off2, (uint16_t)double_floor_to_u32(v));
+                        }
                     }
                 } else {
                     int prev = -0x40000000;
@@ -283,6 +288,14 @@ void build_runs(const int32_t* shifts, int n, int max_rows, ShiftTable& tab, std
         tab.run_unit[r] = 1;
         for (int j = tab.run_first[r] + 1; j < tab.run_first[r + 1]; ++j)
             if (order[j].first != order[j - 1].first + 1) tab.run_unit[r] = 0;
+        // stretches of consecutive integers inside the run (a run may have holes, e.g. -50..9, 11..50)
+        int j = tab.run_first[r];
+        while (j < tab.run_first[r + 1]) {
+            int e = j + 1;
+            while (e < tab.run_first[r + 1] && order[e].first == order[e - 1].first + 1) ++e;
+            for (int q = j; q < e; ++q) tab.seg_end[q] = (short)e;
+            j = e;
+        }
     }
 }
 
