@@ -271,8 +271,7 @@ def _components(flat, cols):
     src, dst = np.concatenate(src), np.concatenate(dst)
     graph = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n))
     count, lab = connected_components(graph, directed=False)
-    first = np.full(count, n, dtype=np.int64)
-    np.minimum.at(first, lab, np.arange(n))
+    _, first = np.unique(lab, return_index=True)               # first (raster-order) pixel of every component
     order = np.argsort(first)
     rank = np.empty(count, dtype=np.int64)
     rank[order] = np.arange(1, count + 1)
