@@ -285,32 +285,46 @@ __device__ __forceinline__ int block_sum_int(int v, int parity, Shared& S) {
 template <int KIND, int kT, int WORDS>
 __device__ __forceinline__ bool fast_select(const double* vals, int n, double med, int t, bool need2, Shared& S) {
     uint32_t cand[WORDS];
+    uint32_t w[WORDS][16];
     int cnt = 0;
+    // one pass builds the candidate masks (finite keys; +-inf are ranked by the caller) and the
+    // bit slices of the HIGH key halves
 #pragma unroll
     for (int q = 0; q < WORDS; ++q) {
         cand[q] = 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int i = (32 * q + e) * kT + (int)threadIdx.x;
-            if (i < n && fabs(key_of<KIND>(vals, i, med)) < INFINITY) cand[q] |= 1u << e;   // +-inf: ranked by the caller
+        for (int e = 0; e < 16; ++e) {
+            const int i0 = (32 * q + e) * kT + (int)threadIdx.x, i1 = (32 * q + e + 16) * kT + (int)threadIdx.x;
+            uint32_t lo = 0, hi = 0;
+            if (i0 < n) {
+                const double x = key_of<KIND>(vals, i0, med);
+                if (fabs(x) < INFINITY) { lo = ordered_key32(x); cand[q] |= 1u << e; }
+            }
+            if (i1 < n) {
+                const double x = key_of<KIND>(vals, i1, med);
+                if (fabs(x) < INFINITY) { hi = ordered_key32(x); cand[q] |= 1u << (e + 16); }
+            }
+            w[q][e] = (lo >> 16) | (hi & 0xFFFF0000u);
         }
+        transpose16x2(w[q]);
         cnt += __popc(cand[q]);
     }
     int m = block_sum_int<kT>(cnt, 0, S);
     int parity = 1;
     for (int round = 0; round < 2 && m > kListCap / 2; ++round) {
-        uint32_t w[WORDS][16];
+        if (round == 1) {                                      // many ties in the high half: slices of the low halves
 #pragma unroll
-        for (int q = 0; q < WORDS; ++q) {
+            for (int q = 0; q < WORDS; ++q) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                uint32_t lo = 0, hi = 0;
-                const int i0 = (32 * q + e) * kT + (int)threadIdx.x, i1 = (32 * q + e + 16) * kT + (int)threadIdx.x;
-                if ((cand[q] >> e) & 1u) lo = ordered_key32(key_of<KIND>(vals, i0, med));
-                if ((cand[q] >> (e + 16)) & 1u) hi = ordered_key32(key_of<KIND>(vals, i1, med));
-                w[q][e] = round == 0 ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+                for (int e = 0; e < 16; ++e) {
+                    uint32_t lo = 0, hi = 0;
+                    const int i0 = (32 * q + e) * kT + (int)threadIdx.x, i1 = (32 * q + e + 16) * kT + (int)threadIdx.x;
+                    if ((cand[q] >> e) & 1u) lo = ordered_key32(key_of<KIND>(vals, i0, med));
+                    if ((cand[q] >> (e + 16)) & 1u) hi = ordered_key32(key_of<KIND>(vals, i1, med));
+                    w[q][e] = (lo & 0xFFFFu) | (hi << 16);
+                }
+                transpose16x2(w[q]);
             }
-            transpose16x2(w[q]);
         }
 #pragma unroll
         for (int L = 0; L < 16; ++L) {
@@ -383,15 +397,30 @@ __device__ __forceinline__ bool fast_select(const double* vals, int n, double me
 
 // value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
 template <int KIND, int kT>
-__device__ void ranked_pair(const double* vals, int n, double med, double lo, double hi, int nneg, int nfin,
+__device__ void ranked_pair(const double* vals, int n, double med, int nneg, int nfin,
                             int t0, int t1, double& v0, double& v1, Shared& S) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
     if (g0 == 0 && g1 == 0) {
         // the common case: both middle ranks are finite values
         constexpr int kWords = kT <= 64 ? 2 : 1;              // 64-thread CTAs own up to 64 elements per thread
-        if (!(n <= 32 * kWords * kT && fast_select<KIND, kT, kWords>(vals, n, med, t0 - nneg, t1 != t0, S)))
-            block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
+        if (n <= 32 * kWords * kT && fast_select<KIND, kT, kWords>(vals, n, med, t0 - nneg, t1 != t0, S)) {
+            v0 = S.dbc[0];
+            v1 = S.dbc[1];
+            __syncthreads();
+            return;
+        }
+    }
+    // generic path (long chords, very many ties, or a middle rank that is +-inf): needs the finite key range
+    double lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += kT) {
+        const double x = key_of<KIND>(vals, i, med);
+        if (fabs(x) < INFINITY) { lo = fmin(lo, x); hi = fmax(hi, x); }
+    }
+    block_minmax(lo, hi, S);
+    __syncthreads();
+    if (g0 == 0 && g1 == 0) {
+        block_select<KIND, kT>(vals, n, med, lo, hi, nfin, t0 - nneg, t1 != t0, S);
         v0 = S.dbc[0];
         v1 = S.dbc[1];
         __syncthreads();
@@ -438,7 +467,6 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     const uint16_t* rp = img + (int64_t)(y - 1) * cols + xa;
 
     // ---- rat = log(img[y]/img[y-1]) -------------------------------------------
-    double fmn = INFINITY, fmx = -INFINITY;
     unsigned int nnan = 0, nneg = 0, npos = 0;
     // 8 independent pixel -> log-table chains in flight per thread (the loop is latency-bound otherwise)
     for (int i0 = threadIdx.x; i0 < n; i0 += kT * 8) {
@@ -458,10 +486,11 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
             if (i < n) {
                 const double r = ta[u] - tb[u];
                 vals[i] = r;
-                if (r != r) ++nnan;
-                else if (r == -INFINITY) ++nneg;
-                else if (r == INFINITY) ++npos;
-                else { fmn = fmin(fmn, r); fmx = fmax(fmx, r); }
+                if (!(fabs(r) < INFINITY)) {                    // a zero pixel in either row: rare
+                    if (r != r) ++nnan;
+                    else if (r < 0) ++nneg;
+                    else ++npos;
+                }
             }
         }
     }
@@ -477,8 +506,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
             if (c) atomicAdd(&S.cnt[2], (unsigned long long)c);
         }
     }
-    block_minmax(fmn, fmx, S);                       // also orders the writes of vals[]
-    __syncthreads();
+    __syncthreads();                                 // counts complete; also orders the writes of vals[]
     const int t_nan = (int)S.cnt[0], t_neg = (int)S.cnt[1], t_pos = (int)S.cnt[2];
     const int nfin = n - t_neg - t_pos;
     if (t_nan > 0) {                                 // np.median -> nan -> everything rejected -> mean([]) = nan
@@ -488,7 +516,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // ---- median (np.median: mean of the two middle values for even n) ---------
     const int t0 = (n - 1) / 2, t1 = n / 2;
     double a0, a1;
-    ranked_pair<0, kT>(vals, n, 0.0, fmn, fmx, t_neg, nfin, t0, t1, a0, a1, S);
+    ranked_pair<0, kT>(vals, n, 0.0, t_neg, nfin, t0, t1, a0, a1, S);
     const double med = t0 == t1 ? a0 : (a0 + a1) / 2.0;
     if (!(fabs(med) < INFINITY)) {                   // |rat - med| contains nan -> mean([]) = nan
         if (threadIdx.x == 0) out[slot] = NAN;
@@ -496,9 +524,8 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     }
     // ---- MAD -------------------------------------------------------------------
     const int ninf = t_neg + t_pos;
-    double dhi = nfin > 0 ? fmax(fabs(fmn - med), fabs(fmx - med)) : 0.0;
     double b0, b1;
-    ranked_pair<1, kT>(vals, n, med, 0.0, dhi, 0, n - ninf, t0, t1, b0, b1, S);
+    ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S);
     const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
     // ---- mean of the inliers ---------------------------------------------------
     double sum = 0.0, cnt = 0.0;
