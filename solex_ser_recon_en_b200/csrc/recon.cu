@@ -9,10 +9,15 @@
 //    shapes TMA cannot describe (row pitch not a multiple of 16 bytes).
 //  * recon_tma_kernel     -- rotated scans.  In raw coordinates the taps of all
 //    shifts for slit column x live in a short run of raw rows around the line,
-//    so a CTA stages [rows of the band] x [TX columns] of one frame into shared
-//    memory with one TMA box per run of shifts (cp.async.bulk.tensor, mbarrier
-//    completion, multi-stage ring), and every thread walks its column through
-//    all shifts.  HBM traffic = band rows once + outputs once.
+//    so a persistent CTA keeps one tile of TX columns and walks frames: each
+//    frame's [band rows] x [TX columns] is staged into shared memory by one TMA
+//    box per run of shifts (cp.async.bulk.tensor, mbarrier completion, 3-4
+//    stage ring).  TX columns x G shift groups of threads: a thread walks a
+//    contiguous slice of the sorted shifts for its column one band row per
+//    shift, converting each tap once.  The image of every shift is addressed
+//    through a table of base pointers, which may point into peer GPUs' memory
+//    (multi-GPU row exchange fused into the store).  HBM traffic = band rows
+//    once + outputs once (ncu: 1.005 x algorithmic).
 // Bound: HBM.  Algorithmic bytes / frame = ih*nb*bytes_per_px + n_shifts*ih*2.
 #include <cuda.h>
 

@@ -3,10 +3,12 @@
 // Stage 1 (shg_transv_row_stats): for every image row y inside the disk, over
 // the chord [xa, xb):   rat = log(img[y] / img[y-1])
 //                       out = mean(rat[|rat - median(rat)| / MAD < 2])
-// One CTA per row.  rat lives in shared memory (or an L2-resident scratch row
-// for very long chords); the two medians are exact order statistics found by a
-// fixed-point radix select (5 bits per level over a monotone 30-bit rescaling
-// of the value range, all-pairs ranking of the last <= 256 candidates).
+// One CTA per (row, image).  rat lives in shared memory (or an L2-resident
+// scratch row for very long chords); the two medians are EXACT order
+// statistics.  Chords of up to 32 elements per thread (every realistic scan)
+// use a binary radix select over monotone 32-bit keys held bit-sliced in
+// registers (fast_select); longer chords, or rows with very many ties, use a
+// fixed-point 5-bits-per-level select over the value range (block_select).
 // log() comes from a 65536-entry fp64 table: pixels are uint16, so
 // log(a/b) = T[a] - T[b] to ~2e-15 absolute (the reference's own log is only
 // good to ~1e-16 relative of a value that is ~1e-2).
@@ -105,7 +107,7 @@ __device__ __noinline__ void block_select(const double* vals, int n, double med,
         constexpr int kCap = kT < kListCap ? kT : kListCap;
         for (; level < 6 && m > kCap; ++level) {
             const int pshift = 30 - 5 * level, bshift = 25 - 5 * level;
-            unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // 32 bins x 8-bit fields ... widened below
+            unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;       // 32 bins x 8-bit fields, flushed into acc[]
             // per-thread counts can exceed 255 for very long rows: flush in chunks of 255 elements
             unsigned int acc[32];
 #pragma unroll
