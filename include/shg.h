@@ -199,7 +199,7 @@ int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, 
  * ratios = [0, stats...] (n values); trend = savgol_filter(ratios, window, 3) with
  * d_coeffs = scipy.signal.savgol_coeffs(window, 3) and cubic end fits; detrended
  * minus its mean; correction = exp(-cumsum); gain[y1:y1+n] = 1 + (correction-1)*taper,
- * 1 elsewhere.  d_stats: n_imgs x (n-1); d_gains: n_imgs x n_rows.  n >= 256. */
+ * 1 elsewhere.  d_stats: n_imgs x (n-1); d_gains: n_imgs x n_rows.  window odd, 5 <= window <= n. */
 int shg_transv_gain(const double* d_stats, int n_imgs, int n, int window, const double* d_coeffs,
                     const double* d_taper, int y1, int n_rows, double* d_gains, void* stream);
 /* out[i][r][c] = trunc(min(img[i][r][c] * gain[i][r], 65535)), images at stride img_stride */

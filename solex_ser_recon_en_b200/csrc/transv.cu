@@ -666,10 +666,11 @@ transv_gain_kernel(const double* __restrict__ stats /* [n_imgs][n-1] */, int n, 
     double run = 0.0;
     for (int i = a; i < b; ++i) { run += d[i] - mean; r[i] = run; }
     __syncthreads();
-    d[threadIdx.x] = run;                                       // chunk totals (d[] is no longer needed; n >= kGT)
+    double* totals = sol + 4;                                   // kGT chunk totals
+    totals[threadIdx.x] = run;
     __syncthreads();
     double off = 0.0;
-    for (int q = 0; q < (int)threadIdx.x; ++q) off += d[q];
+    for (int q = 0; q < (int)threadIdx.x; ++q) off += totals[q];
     for (int i = a; i < b; ++i) {
         const double corr = exp(-(r[i] + off));
         g[y1 + i] = 1.0 + (corr - 1.0) * taper[i];
@@ -802,9 +803,8 @@ extern "C" int shg_transv_gain(const double* d_stats, int n_imgs, int n, int win
                                const double* d_taper, int y1, int n_rows, double* d_gains, void* stream) {
     if (n_imgs <= 0) return 0;
     SHG_REQUIRE(window >= 5 && (window & 1) && window <= n, "shg_transv_gain: window %d for %d rows", window, n);
-    SHG_REQUIRE(y1 >= 0 && y1 + n <= n_rows && n >= kGT / 32, "shg_transv_gain: rows [%d, %d) outside the image", y1, y1 + n);
-    SHG_REQUIRE(n >= kGT, "shg_transv_gain: needs at least %d rows (shorter vectors are done on the host)", kGT);
-    const size_t smem = ((size_t)2 * n + 96 + 4) * sizeof(double);
+    SHG_REQUIRE(y1 >= 0 && y1 + n <= n_rows, "shg_transv_gain: rows [%d, %d) outside the image", y1, y1 + n);
+    const size_t smem = ((size_t)2 * n + 96 + 4 + kGT) * sizeof(double);
     int dev = 0, optin = 0;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -259,15 +259,20 @@ def _components(flat, cols):
     from scipy.sparse.csgraph import connected_components
     n = len(flat)
     col = flat % cols
-    src, dst = [], []
-    for dr, dc in ((0, 1), (1, -1), (1, 0), (1, 1)):
-        ok = (col + dc >= 0) & (col + dc < cols)
-        target = flat + dr * cols + dc
-        pos = np.searchsorted(flat, target)
-        pos_c = np.minimum(pos, n - 1)
-        hit = ok & (pos < n) & (flat[pos_c] == target)
-        src.append(np.nonzero(hit)[0])
-        dst.append(pos_c[hit])
+    idx = np.arange(n)
+    # right neighbour: the next element of the sorted array
+    right = np.flatnonzero((flat[1:] == flat[:-1] + 1) & (col[:-1] + 1 < cols))
+    src, dst = [right], [right + 1]
+    # the three neighbours in the next row are consecutive flat indices t, t+1, t+2 (t = below-left):
+    # one binary search, then look at the (at most three) entries that follow
+    t = flat + cols - 1
+    pos = np.searchsorted(flat, t)
+    for k in range(3):
+        p = np.minimum(pos + k, n - 1)
+        d = flat[p] - t                                  # 0: below-left, 1: below, 2: below-right
+        hit = (pos + k < n) & (d >= 0) & (d <= 2) & (col + d - 1 >= 0) & (col + d - 1 < cols)
+        src.append(idx[hit])
+        dst.append(p[hit])
     src, dst = np.concatenate(src), np.concatenate(dst)
     graph = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n))
     count, lab = connected_components(graph, directed=False)
@@ -339,7 +344,13 @@ def limb_points_device(eng, sums, sigma=2.0):
     sel = np.isin(lab, chosen)
     flat_sel = flat_e[sel]
     pts = np.stack([flat_sel // cols, flat_sel % cols], axis=1)
-    hull_flat = flat_sel[ConvexHull(pts).vertices]
+    # hull vertices are extreme points, and every extreme point is the first or last pixel of its row:
+    # the hull of those (<= 2 per row) has the same vertices as the hull of all points
+    row_start = np.flatnonzero(np.diff(pts[:, 0], prepend=-1))
+    row_last = np.append(row_start[1:] - 1, len(pts) - 1)
+    ends = np.unique(np.concatenate([row_start, row_last]))
+    hull_flat = flat_sel[ends[ConvexHull(pts[ends]).vertices]] if len(ends) >= 3 else \
+        flat_sel[ConvexHull(pts).vertices]
     kept = np.zeros(len(flat_e), bool)
     for c in chosen:
         region = lab == c

@@ -589,14 +589,12 @@ class Engine:
 
     def transversalium_gains(self, stats_dev, y1: int, y2: int, n_rows: int, strength: int):
         """(S, n_rows) device tensor of per-row gains from the (S, n-1) device row
-        statistics (solex_util.py:400-404, 456-479).  Vectors too short for the
-        kernel (a Sun < 256 rows) go through the same arithmetic on the host."""
-        from .solex_util import savgol_window, transversalium_gains, tukey_taper
+        statistics (solex_util.py:400-404, 456-479)."""
+        from .solex_util import savgol_window, tukey_taper
         n = y2 - y1
         window = savgol_window(n, strength)
-        if n < 256 or window < 5:
-            g = transversalium_gains(stats_dev.cpu().numpy(), y1, y2, n_rows, strength)
-            return torch.from_numpy(g).to(self.device)
+        if window < 5:                     # scipy.signal.savgol_filter: polyorder (3) must be less than window_length
+            raise ValueError('polyorder must be less than window_length (only %d disk rows)' % n)
         from scipy.signal import savgol_coeffs
         key = (n, window)
         if getattr(self, '_gain_tab_key', None) != key:

@@ -485,7 +485,7 @@ def test_limb_building_blocks(eng):
     assert np.array_equal(eng.blur_hist(box, scale, ceiling, edges), counts)
 
 
-@pytest.mark.parametrize('n,strength', [(3276, 301), (700, 301), (300, 301), (256, 301), (257, 9)])
+@pytest.mark.parametrize('n,strength', [(3276, 301), (700, 301), (300, 301), (256, 301), (257, 9), (100, 301), (40, 301), (7, 301), (6, 5)])
 def test_gain_kernel_matches_reference_arithmetic(eng, n, strength):
     """savgol trend + detrend + exp(-cumsum) + taper on the device against the
     oracle's scipy / numpy version of the same lines (tolerance: north_star's 1e-5; measured ~1e-12)."""
