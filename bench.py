@@ -297,9 +297,23 @@ def run_b200(a):
             r = memory_scan(host_ptr - k0 * geom.frame_bytes, a.width, a.height, 16, a.frames)
             r.device_stack = stack                      # refill the same HBM buffer (pinned-buffer / HBM reuse)
             return r
+        # PCIe roofline denominator, measured in this run: one large pinned H2D copy, best of 3
+        probe = min(nbytes, 4 << 30)
+        best = None
+        for _ in range(3):
+            p0 = torch.cuda.Event(enable_timing=True)
+            p1 = torch.cuda.Event(enable_timing=True)
+            p0.record()
+            eng.copy(stack.frames.data_ptr(), host_ptr, probe, 'h2d')
+            p1.record()
+            torch.cuda.synchronize()
+            t = p0.elapsed_time(p1)
+            best = t if best is None else min(best, t)
+        pcie_peak = probe / (best * 1e-3) / 1e9
         e_steps = a.e2e_steps or a.steps
         e2e = timed_loop(host_reader, e_steps, min(a.warmup, 3), True, 'e2e')
         e2e['h2d'] = a.frames * geom.frame_bytes
+        e2e['pcie_peak'] = pcie_peak
         if world > 1:
             t = torch.tensor([float(e2e['d2h'])], dtype=torch.float64, device='cuda')
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -359,6 +373,8 @@ def run_b200(a):
                            'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
                            'ms_per_step': e2e['ms_per_step'],
                            'h2d_GBps': e2e['h2d'] / (e2e['ms_per_step'] * 1e-3) / 1e9,
+                           'pcie_h2d_peak_GBps_per_gpu': e2e['pcie_peak'],
+                           'pcie_frac': e2e['h2d'] / (e2e['ms_per_step'] * 1e-3) / 1e9 / (e2e['pcie_peak'] * world),
                            'stages_ms': {k: round(v, 3) for k, v in sorted(e2e['stages'].items())}}
         if world == 1 and not a.no_cpu:
             line['cpu_baseline'] = cpu_baseline_subprocess(a)
