@@ -5,6 +5,7 @@ are compared with the oracle on the same file (seconds of NumPy); configs 3-5
 are too big for the CPU oracle, so they are checked through size-independent
 properties of a device-synthesised scan: linearity of the integer sums over
 frame ranges, bit-exact disks on sampled frames, and shard-invariance."""
+import math
 import os
 
 import numpy as np
@@ -96,3 +97,62 @@ def test_big_geometry_properties(geom, n_shift):
     mo, xo = O.finalize_mean_max(st.sum.cpu().numpy().view(np.uint64).reshape(H, W),
                                  st.max.cpu().numpy().reshape(H, W).astype(np.uint16), N, False)
     assert np.array_equal(mean_img.cpu().numpy(), mo) and np.array_equal(max_img.cpu().numpy(), xo)
+
+
+def test_config5_full_size_against_oracle_on_one_shift(tmp_path):
+    """BASELINE configs[4] at its real size (20 000 frames x 4096x512, 84 GB in HBM), through the drop-in entry
+    points.  The CPU oracle cannot read 84 GB, so: the integer mean frame is checked by linearity against four
+    frame-range shards; the disks are checked bit-exactly on sampled frames; and ONE complete disk image is copied
+    back and pushed through the oracle's ellipse fit, warp and transversalium for a full-size comparison of the
+    post-processing (<= 1 DN, gains 1e-5)."""
+    import torch
+    from solex_ser_recon_en_b200 import Solex_recon
+    from solex_ser_recon_en_b200.engine import ScanGeometry, get_engine
+    from solex_ser_recon_en_b200.video_reader import device_scan
+    eng = get_engine(0)
+    free, _ = torch.cuda.mem_get_info()
+    N = 20000 if free > 120e9 else 4000
+    g = ScanGeometry(4096, 512, 2, N)
+    st = eng.synth_stack(g, seed=5)
+    got = {}
+
+    def sink(basefich, image, cercle):
+        got[int(basefich.rsplit('_shift=', 1)[1])] = image
+
+    opt = _options(tmp_path, shift=[0, -50, 50], _result_sink=sink)
+    disk_list, bounds, hdr = Solex_recon.solex_read_reader(device_scan(st), opt, os.path.join(str(tmp_path), 'cfg5'))
+    # pass 1: four shards add up to the same integers
+    total = st.sum.clone()
+    acc = torch.zeros_like(total)
+    for q in range(4):
+        part = eng.synth_stack(g, k0=q * N // 4, n=N // 4, seed=5)
+        eng.accumulate(part)
+        acc += part.sum
+        del part
+    assert torch.equal(acc, total)
+    # pass 2: sampled frames of every disk, bit-exact
+    lf_fit = None
+    ks = [0, 1, N // 2, N - 1]
+    frames = np.stack([st.host_frames(k, k + 1)[0] for k in ks])
+    mean_img, max_img = eng.finalize_mean_max(st.sum, st.max, N, g)
+    det = eng.detect_line(mean_img, max_img)
+    lf_fit = eng.fit_line(det, g.ih)['fit']
+    ref = O.recon(frames, lf_fit, opt['shift'])
+    for i in range(len(opt['shift'])):
+        img = disk_list[i].tensor.view(torch.int16)[ks].cpu().numpy().view(np.uint16)
+        assert np.array_equal(img.T, ref[i]), opt['shift'][i]
+    # post-processing of the whole set on the GPU ...
+    Solex_recon.solex_process(opt, disk_list, bounds, hdr)
+    # ... and of shift 0 on the CPU oracle, from the GPU's own disk images
+    disk10 = np.asarray(disk_list[0])
+    disk0 = np.asarray(disk_list[1])
+    _, circle, ratio, phi, borders = O.ellipse_to_circle(disk10)
+    np.testing.assert_allclose(float(opt['ratio_fixe']), ratio, rtol=1e-9)
+    np.testing.assert_allclose(math.radians(float(opt['slant_fix'])), phi, rtol=1e-6, atol=1e-12)
+    circ, _ = O.warp_rows(disk0, phi, ratio)
+    det_ref, gain_ref = O.correct_transversalium(circ, circle, borders)
+    det_gpu = np.asarray(got[0])
+    assert det_gpu.shape == det_ref.shape
+    d = np.abs(det_gpu.astype(np.int32) - det_ref.astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) < 1e-3
+    np.testing.assert_allclose(opt['_transversalium_gains'][0], gain_ref, rtol=1e-5)
