@@ -178,6 +178,11 @@ int shg_nms_candidates(const double* d_gi, const double* d_gj, const double* d_m
                        double low, uint32_t* d_count, uint32_t cap, uint32_t* d_list_idx,
                        double* d_list_mag, void* stream);
 
+/* HOST helper (no GPU): 8-connected components of a sparse pixel list (flat = row*cols + col,
+ * strictly ascending), labelled 1.. in raster order of each component's first pixel, i.e. what
+ * scipy.ndimage.label(edges, ones((3,3))) gives on those pixels (reference ellipse_to_circle.py:252). */
+int shg_label_points(const int64_t* h_flat, int64_t n, int64_t cols, int32_t* h_labels, int32_t* h_n_labels);
+
 /* ---- a12: transversalium (reference solex_util.py:76-86,383-395,489-516) */
 /* tab[v] = log(v) for v in [0, 65536) (tab[0] = -inf): pixels are uint16, so
  * the reference's log(img[y]/img[y-1]) is tab[a] - tab[b] to ~2e-15 absolute. */

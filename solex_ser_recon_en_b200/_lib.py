@@ -55,6 +55,7 @@ _PROTOS = {
     'shg_flood_smooth': (i32, [vp, i32, i32, dbl, dbl, C.POINTER(dbl), i32, dbl, vp, vp, vp]),
     'shg_sobel_mag': (i32, [vp, i32, i32, vp, vp, vp, vp]),
     'shg_nms_candidates': (i32, [vp, vp, vp, i32, i32, dbl, vp, C.c_uint32, vp, vp, vp]),
+    'shg_label_points': (i32, [vp, i64, i64, vp, C.POINTER(C.c_int32)]),
     'shg_log_table': (i32, [vp, vp]),
     'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),
     'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]),

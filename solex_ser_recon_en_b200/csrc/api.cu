@@ -1,6 +1,8 @@
 // libshg: status, version, device query.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -59,5 +61,41 @@ extern "C" int shg_ipc_open(const unsigned char* handle64, void** d_ptr) {
 
 extern "C" int shg_ipc_close(void* d_ptr) {
     if (d_ptr) SHG_CHECK(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+// ---- host helper: 8-connected components of a sparse, sorted pixel list -----
+// (scipy.ndimage.label semantics on the thin-edge pixels of the limb search,
+// reference ellipse_to_circle.py:252: labels 1.. numbered in raster order of each
+// component's first pixel).  flat = row*cols + col, strictly ascending.  Pure
+// host code: the list has ~10^4 entries.
+extern "C" int shg_label_points(const int64_t* flat, int64_t n, int64_t cols, int32_t* labels, int32_t* n_labels) {
+    SHG_REQUIRE(flat && labels && n_labels && n >= 0 && cols > 0, "shg_label_points: bad arguments");
+    std::vector<int32_t> parent((size_t)n);
+    auto find = [&](int32_t a) {
+        while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+        return a;
+    };
+    auto unite = [&](int32_t a, int32_t b) {
+        a = find(a); b = find(b);
+        if (a != b) parent[a > b ? a : b] = a > b ? b : a;          // keep the earliest pixel as the root
+    };
+    int64_t j = 0;                                                   // first point that can be an upper neighbour
+    for (int64_t i = 0; i < n; ++i) {
+        SHG_REQUIRE(i == 0 || flat[i] > flat[i - 1], "shg_label_points: indices must be strictly ascending");
+        parent[i] = (int32_t)i;
+        const int64_t col = flat[i] % cols;
+        if (i > 0 && col > 0 && flat[i - 1] == flat[i] - 1) unite((int32_t)i, (int32_t)(i - 1));
+        const int64_t lo = flat[i] - cols - (col > 0 ? 1 : 0), hi = flat[i] - cols + (col + 1 < cols ? 1 : 0);
+        while (j < i && flat[j] < lo) ++j;
+        for (int64_t q = j; q < i && flat[q] <= hi; ++q) unite((int32_t)i, (int32_t)q);
+    }
+    int32_t next = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t r = find((int32_t)i);
+        if (r == (int32_t)i) labels[i] = ++next;                     // roots are first pixels: raster order
+        else labels[i] = labels[r];
+    }
+    *n_labels = next;
     return 0;
 }

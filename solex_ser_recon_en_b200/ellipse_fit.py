@@ -254,33 +254,15 @@ def flood_level(counts, edges, fallback):
 
 def _components(flat, cols):
     """8-connected components of a sorted array of flat pixel indices; labels are
-    numbered 1.. in raster order of each component's first pixel (scipy.ndimage.label)."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
-    n = len(flat)
-    col = flat % cols
-    idx = np.arange(n)
-    # right neighbour: the next element of the sorted array
-    right = np.flatnonzero((flat[1:] == flat[:-1] + 1) & (col[:-1] + 1 < cols))
-    src, dst = [right], [right + 1]
-    # the three neighbours in the next row are consecutive flat indices t, t+1, t+2 (t = below-left):
-    # one binary search, then look at the (at most three) entries that follow
-    t = flat + cols - 1
-    pos = np.searchsorted(flat, t)
-    for k in range(3):
-        p = np.minimum(pos + k, n - 1)
-        d = flat[p] - t                                  # 0: below-left, 1: below, 2: below-right
-        hit = (pos + k < n) & (d >= 0) & (d <= 2) & (col + d - 1 >= 0) & (col + d - 1 < cols)
-        src.append(idx[hit])
-        dst.append(p[hit])
-    src, dst = np.concatenate(src), np.concatenate(dst)
-    graph = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n))
-    count, lab = connected_components(graph, directed=False)
-    _, first = np.unique(lab, return_index=True)               # first (raster-order) pixel of every component
-    order = np.argsort(first)
-    rank = np.empty(count, dtype=np.int64)
-    rank[order] = np.arange(1, count + 1)
-    return count, rank[lab]
+    numbered 1.. in raster order of each component's first pixel (scipy.ndimage.label).
+    A union-find over the sorted list in libshg (host code; ~10^4 points)."""
+    import ctypes as C
+    from ._lib import call
+    flat = np.ascontiguousarray(flat, dtype=np.int64)
+    labels = np.empty(len(flat), dtype=np.int32)
+    count = C.c_int32(0)
+    call('shg_label_points', flat.ctypes.data, len(flat), int(cols), labels.ctypes.data, C.byref(count))
+    return int(count.value), labels.astype(np.int64)
 
 
 def limb_points_device(eng, sums, sigma=2.0):
