@@ -41,3 +41,18 @@ def test_engine_fails_loudly_without_a_gpu():
     from solex_ser_recon_en_b200._lib import ShgError
     with pytest.raises(ShgError):
         Engine(0)
+
+
+def test_label_points_matches_scipy_label():
+    """The host-side labelling helper (no GPU needed) against scipy.ndimage.label."""
+    import numpy as np
+    from scipy import ndimage as ndi
+    from solex_ser_recon_en_b200 import ellipse_fit as E
+    rng = np.random.default_rng(0)
+    for t in range(100):
+        rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 50))
+        m = rng.random((rows, cols)) < rng.uniform(0.05, 0.7)
+        lab, cnt = ndi.label(m, np.ones((3, 3)))
+        flat = np.flatnonzero(m)
+        c2, l2 = E._components(flat, cols)
+        assert c2 == cnt and np.array_equal(l2, lab.ravel()[flat]), t
