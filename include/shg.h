@@ -153,10 +153,11 @@ int shg_downscale4_sum(const uint16_t* d_disk, int64_t n_frames, int ih, int fli
 int shg_box_sum_u32(const uint32_t* d_in, int rows, int cols, int kw, int kh, uint32_t* d_out,
                     uint32_t* d_tmp, void* stream);
 int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, void* stream);
-/* exact order statistics: h_out[q] = the h_ranks[q]-th smallest (0-based) of d_vals.
- * Blocking (reads four 256-bin histograms back per rank).  d_work256: 256 uint32. */
+/* exact order statistics: h_out[q] = the h_ranks[q]-th smallest (0-based) of d_vals, for up to 8
+ * ranks at once (byte-wise radix select, state kept on the device).  Blocking: one synchronisation,
+ * for the read-back of the results.  d_work: 2112 uint32 (8448 bytes) of device scratch. */
 int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
-                   uint32_t* h_out, uint32_t* d_work256, void* stream);
+                   uint32_t* h_out, uint32_t* d_work, void* stream);
 /* blurred = (B * 2^-20) * scale.  d_out2 = {min B, max B} over pixels with blurred < ceiling */
 int shg_blur_range(const uint32_t* d_box, int64_t n, double scale, double ceiling, uint32_t* d_out2, void* stream);
 /* np.histogram(blurred[blurred < ceiling], bins=n_bins) given its n_bins+1 edges; d_counts: 32 uint64 */

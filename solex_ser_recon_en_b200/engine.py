@@ -487,9 +487,9 @@ class Engine:
         ranks = [int(r) for r in ranks]
         r = (C.c_int64 * len(ranks))(*ranks)
         out = (C.c_uint32 * len(ranks))()
-        work = self.empty((256,), torch.int32)
+        work = self.empty((2112,), torch.int32)
         call('shg_select_u32', vals.data_ptr(), vals.numel(), r, len(ranks), out, work.data_ptr(), self.stream)
-        self.n_launches += 4 * len(ranks)
+        self.n_launches += 8
         return [int(v) for v in out]
 
     def blur_range(self, box, scale: float, ceiling: float):
