@@ -109,29 +109,33 @@ radix_hist_multi_kernel(const uint32_t* __restrict__ v, int64_t n, const uint32_
         if (h[r][threadIdx.x]) atomicAdd(&hist[r * 256 + threadIdx.x], h[r][threadIdx.x]);
 }
 
-// one thread per rank: walk the 256 bins, extend the prefix, reduce the rank; clears the histograms
-__global__ void radix_step_kernel(uint32_t* __restrict__ prefix, long long* __restrict__ rank, int n_ranks,
-                                  unsigned int* __restrict__ hist) {
+// extend every rank's prefix by the byte whose bin contains it; clears the histograms for the next pass
+__global__ void __launch_bounds__(256)
+radix_step_kernel(uint32_t* __restrict__ prefix, long long* __restrict__ rank, int n_ranks,
+                  unsigned int* __restrict__ hist) {
     __shared__ uint32_t old_pf[SelectState::kMaxRanks];
-    const int r = threadIdx.x;
-    if (r < n_ranks) old_pf[r] = prefix[r];
+    __shared__ unsigned int h[SelectState::kMaxRanks][256];
+    const int t = threadIdx.x;
+    if (t < n_ranks) old_pf[t] = prefix[t];
+    for (int r = 0; r < n_ranks; ++r) {
+        h[r][t] = hist[r * 256 + t];
+        hist[r * 256 + t] = 0;
+    }
     __syncthreads();
-    if (r < n_ranks) {
-        int src = r;                                       // histogram owner: first rank with the same prefix
-        for (int q = r - 1; q >= 0; --q)
-            if (old_pf[q] == old_pf[r]) src = q;
-        long long left = rank[r];
+    if (t < n_ranks) {
+        int src = t;                                       // histogram owner: first rank with the same prefix
+        for (int q = t - 1; q >= 0; --q)
+            if (old_pf[q] == old_pf[t]) src = q;
+        long long left = rank[t];
         int b = 0;
         for (; b < 255; ++b) {
-            const long long c = hist[src * 256 + b];
+            const long long c = h[src][b];
             if (left < c) break;
             left -= c;
         }
-        prefix[r] = (old_pf[r] << 8) | (uint32_t)b;
-        rank[r] = left;
+        prefix[t] = (old_pf[t] << 8) | (uint32_t)b;
+        rank[t] = left;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_ranks * 256; i += blockDim.x) hist[i] = 0;
 }
 
 // blurred(B) = (B * 2^-20) * scale, exactly as cv2.blur computes it from image/65536
