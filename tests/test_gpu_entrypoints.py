@@ -175,3 +175,36 @@ def test_solex_process_batched_path_matches_per_image_path(tmp_path):
         d = np.abs(det.astype(np.int32) - g[f'det_{sh}'].astype(np.int32))
         assert d.max() <= 1 and np.mean(d != 0) < 1e-3
         np.testing.assert_allclose(opt['_transversalium_gains'][sh], g[f'gain_{sh}'], rtol=1e-5)
+
+
+def test_resident_scan_is_reconstructed_again_without_reingest(tmp_path):
+    """The spectral-analyser pattern (reference spectralAnalyserUI.py:345-346): the same scan
+    reconstructed again at new shifts.  With options['_keep_stack'] the stack stays in HBM and the
+    second read_video_improved costs one kernel, not another pass over the file."""
+    from oracle import shg_oracle as O
+    from solex_ser_recon_en_b200 import solex_util, video_reader
+    from solex_ser_recon_en_b200.engine import get_engine
+    from helpers import case_stack
+    g = golden('ser16_rot')
+    _, stack = case_stack('ser16_rot')
+    path = case_file('ser16_rot', tmp_path)
+    opt = options_for('ser16_rot', tmp_path, _nolog=True, _keep_stack=True)
+    opt['shift'] = [10, 0]
+    rdr = video_reader.video_reader(path)
+    mean_img, fit, y1, y2 = solex_util.compute_mean_return_fit(rdr, opt, {}, rdr.iw, rdr.ih, os.path.splitext(path)[0])
+    assert np.array_equal(mean_img, g['mean_img'])
+    eng = get_engine()
+    real_ingest = eng.ingest_file
+    calls = []
+    eng.ingest_file = lambda *a, **k: (calls.append(1), real_ingest(*a, **k))[1]
+    try:
+        for shifts in ([10, 0], [-7, 3, 12], [1]):
+            opt['shift'] = shifts
+            disks, ih, iw, n = solex_util.read_video_improved(video_reader.video_reader(path), fit, opt)
+            ref = O.recon(stack, fit, shifts)
+            for i in range(len(shifts)):
+                assert np.array_equal(np.asarray(disks[i]), ref[i]), shifts[i]
+    finally:
+        eng.ingest_file = real_ingest
+        solex_util.release_resident()
+    assert calls == []
