@@ -71,7 +71,8 @@ def solex_read_reader(rdr, options, basefich0):
     options['shift'] = list(dict.fromkeys([options['ellipse_fit_shift'], 0] + options['shift']))
     hdr = make_header(rdr)
     mean_img, fit, backup_y1, backup_y2 = compute_mean_return_fit(rdr, options, hdr, rdr.iw, rdr.ih, basefich0)
-    options['_prefetch_fit'] = True          # solex_process follows: start the limb search under the reconstruction
+    if not os.environ.get('SHG_NO_EARLY_FIT'):   # solex_process follows: start the limb search under the reconstruction
+        options['_prefetch_fit'] = True
     try:
         disk_list, ih, iw, _ = read_video_improved(rdr, fit, options)
     finally:
