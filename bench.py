@@ -368,6 +368,15 @@ def run_b200(a):
                          'algorithmic_bytes_per_launch': acc_bytes, 'ms_per_launch': t_acc,
                          'ms_per_launch_inside_step': in_step, 'frac_of_8TBps_nominal': achieved / 8000.0},
         }
+        # secondary roofline: pass 2 (reconstruction), algorithmic bytes of SURVEY 8(d) over its stage time
+        nb = shifts[-1] - shifts[0] + 2
+        recon_bytes = (k1 - k0) * (geom.ih * nb * 2 + len(shifts) * geom.ih * 2)
+        t_rec = dev['stages'].get('recon+gather')
+        if t_rec:
+            line['roofline_recon'] = {'bound': 'hbm' if world == 1 else 'hbm+nvlink', 'kernel': 'recon_tma_kernel',
+                                      'achieved': recon_bytes / (t_rec * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                      'frac': recon_bytes / (t_rec * 1e-3) / 1e9 / peak,
+                                      'algorithmic_bytes_per_launch': recon_bytes, 'ms_in_step': t_rec}
         if e2e is not None:
             line['e2e'] = {'value': a.frames / (e2e['ms_per_step'] * 1e-3), 'unit': 'frames/s',
                            'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'],
