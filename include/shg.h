@@ -153,9 +153,10 @@ int shg_downscale4_sum(const uint16_t* d_disk, int64_t n_frames, int ih, int fli
 int shg_box_sum_u32(const uint32_t* d_in, int rows, int cols, int kw, int kh, uint32_t* d_out,
                     uint32_t* d_tmp, void* stream);
 int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, void* stream);
-/* exact order statistics: h_out[q] = the h_ranks[q]-th smallest (0-based) of d_vals, for up to 8
- * ranks at once (byte-wise radix select, state kept on the device).  Blocking: one synchronisation,
- * for the read-back of the results.  d_work: 2112 uint32 (8448 bytes) of device scratch. */
+/* exact order statistics: h_out[q] = the h_ranks[q]-th smallest (0-based) of d_vals (byte-wise radix
+ * select; ranks that share a prefix share a pass).  Blocking: reads a 256-bin histogram back per pass
+ * (keeping the state on the device and queueing all passes was measured SLOWER when the limb search
+ * runs underneath the reconstruction kernel).  d_work: at least 256 uint32 of device scratch. */
 int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
                    uint32_t* h_out, uint32_t* d_work, void* stream);
 /* blurred = (B * 2^-20) * scale.  d_out2 = {min B, max B} over pixels with blurred < ceiling */

@@ -78,66 +78,6 @@ radix_hist_kernel(const uint32_t* __restrict__ v, int64_t n, uint32_t prefix, in
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
-// ---- multi-rank radix select with the state on the device (no host round trips) ----
-struct SelectState {                    // lives in d_work: [n_ranks] prefixes, [n_ranks] ranks, then histograms
-    static constexpr int kMaxRanks = 8;
-};
-
-// histograms of byte `shift/8` for every rank whose prefix matches (hist[r][256])
-__global__ void __launch_bounds__(256)
-radix_hist_multi_kernel(const uint32_t* __restrict__ v, int64_t n, const uint32_t* __restrict__ prefix, int n_ranks,
-                        int shift, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int h[SelectState::kMaxRanks][256];
-    __shared__ uint32_t pf[SelectState::kMaxRanks];
-    for (int r = 0; r < n_ranks; ++r) h[r][threadIdx.x] = 0;
-    if (threadIdx.x < n_ranks) pf[threadIdx.x] = prefix[threadIdx.x];
-    __syncthreads();
-    const int hi_shift = shift + 8;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const uint32_t k = v[i];
-        const uint32_t top = hi_shift >= 32 ? 0u : (k >> hi_shift);
-        const uint32_t b = (k >> shift) & 255u;
-        for (int r = 0; r < n_ranks; ++r) {
-            // ranks that share a prefix share the histogram of the first of them
-            bool dup = false;
-            for (int q = 0; q < r; ++q) dup |= pf[q] == pf[r];
-            if (!dup && (hi_shift >= 32 || top == pf[r])) atomicAdd(&h[r][b], 1u);
-        }
-    }
-    __syncthreads();
-    for (int r = 0; r < n_ranks; ++r)
-        if (h[r][threadIdx.x]) atomicAdd(&hist[r * 256 + threadIdx.x], h[r][threadIdx.x]);
-}
-
-// extend every rank's prefix by the byte whose bin contains it; clears the histograms for the next pass
-__global__ void __launch_bounds__(256)
-radix_step_kernel(uint32_t* __restrict__ prefix, long long* __restrict__ rank, int n_ranks,
-                  unsigned int* __restrict__ hist) {
-    __shared__ uint32_t old_pf[SelectState::kMaxRanks];
-    __shared__ unsigned int h[SelectState::kMaxRanks][256];
-    const int t = threadIdx.x;
-    if (t < n_ranks) old_pf[t] = prefix[t];
-    for (int r = 0; r < n_ranks; ++r) {
-        h[r][t] = hist[r * 256 + t];
-        hist[r * 256 + t] = 0;
-    }
-    __syncthreads();
-    if (t < n_ranks) {
-        int src = t;                                       // histogram owner: first rank with the same prefix
-        for (int q = t - 1; q >= 0; --q)
-            if (old_pf[q] == old_pf[t]) src = q;
-        long long left = rank[t];
-        int b = 0;
-        for (; b < 255; ++b) {
-            const long long c = h[src][b];
-            if (left < c) break;
-            left -= c;
-        }
-        prefix[t] = (old_pf[t] << 8) | (uint32_t)b;
-        rank[t] = left;
-    }
-}
-
 // blurred(B) = (B * 2^-20) * scale, exactly as cv2.blur computes it from image/65536
 __device__ __forceinline__ double blurred_of(uint32_t b, double scale) {
     return __dmul_rn(__dmul_rn((double)b, 9.5367431640625e-07), scale);
@@ -296,27 +236,40 @@ extern "C" int shg_sum_u32(const uint32_t* d_in, int64_t n, uint64_t* d_out, voi
 }
 
 extern "C" int shg_select_u32(const uint32_t* d_vals, int64_t n, const int64_t* h_ranks, int n_ranks,
-                              uint32_t* h_out, uint32_t* d_work, void* stream) {
-    SHG_REQUIRE(n > 0 && n_ranks >= 0 && n_ranks <= SelectState::kMaxRanks,
-                "shg_select_u32: empty input or more than %d ranks", SelectState::kMaxRanks);
-    if (n_ranks == 0) return 0;
+                              uint32_t* h_out, uint32_t* d_work256, void* stream) {
+    SHG_REQUIRE(n > 0 && n_ranks >= 0 && n_ranks <= 64, "shg_select_u32: empty input or too many ranks");
     cudaStream_t st = as_stream(stream);
+    unsigned int hist[256];
+    std::vector<int64_t> rank(h_ranks, h_ranks + n_ranks);
+    std::vector<uint32_t> prefix(n_ranks, 0);
     for (int q = 0; q < n_ranks; ++q)
-        SHG_REQUIRE(h_ranks[q] >= 0 && h_ranks[q] < n, "shg_select_u32: rank %lld out of range", (long long)h_ranks[q]);
-    // device state: prefixes | ranks | histograms; four byte-wide passes, MSB first, all queued on the
-    // stream; the only synchronisation is the final read-back of the prefixes (= the selected values)
-    uint32_t* d_prefix = d_work;
-    long long* d_rank = reinterpret_cast<long long*>(d_work + 16);
-    unsigned int* d_hist = d_work + 64;
-    SHG_CHECK(cudaMemsetAsync(d_work, 0, (64 + (size_t)SelectState::kMaxRanks * 256) * 4, st));
-    SHG_CHECK(cudaMemcpyAsync(d_rank, h_ranks, (size_t)n_ranks * 8, cudaMemcpyHostToDevice, st));
+        SHG_REQUIRE(rank[q] >= 0 && rank[q] < n, "shg_select_u32: rank %lld out of range", (long long)rank[q]);
+    // MSB-first, one byte per pass; ranks that still share a prefix (the two middle elements of a
+    // median, the two neighbours of a percentile) share the histogram of that pass
     for (int shift = 24; shift >= 0; shift -= 8) {
-        radix_hist_multi_kernel<<<grid_for(n), 256, 0, st>>>(d_vals, n, d_prefix, n_ranks, shift, d_hist);
-        radix_step_kernel<<<1, 256, 0, st>>>(d_prefix, d_rank, n_ranks, d_hist);
+        std::vector<char> done(n_ranks, 0);
+        for (int q = 0; q < n_ranks; ++q) {
+            if (done[q]) continue;
+            SHG_CHECK(cudaMemsetAsync(d_work256, 0, 256 * 4, st));
+            radix_hist_kernel<<<grid_for(n), 256, 0, st>>>(d_vals, n, prefix[q], shift, d_work256);
+            SHG_LAUNCH_CHECK();
+            SHG_CHECK(cudaMemcpyAsync(hist, d_work256, 256 * 4, cudaMemcpyDeviceToHost, st));
+            SHG_CHECK(cudaStreamSynchronize(st));
+            const uint32_t group = prefix[q];
+            for (int p = q; p < n_ranks; ++p) {
+                if (done[p] || prefix[p] != group) continue;
+                int b = 0;
+                for (; b < 256; ++b) {
+                    if (rank[p] < (int64_t)hist[b]) break;
+                    rank[p] -= hist[b];
+                }
+                SHG_REQUIRE(b < 256, "shg_select_u32: internal error (histogram does not cover the rank)");
+                prefix[p] = (group << 8) | (uint32_t)b;
+                done[p] = 1;
+            }
+        }
     }
-    SHG_LAUNCH_CHECK();
-    SHG_CHECK(cudaMemcpyAsync(h_out, d_prefix, (size_t)n_ranks * 4, cudaMemcpyDeviceToHost, st));
-    SHG_CHECK(cudaStreamSynchronize(st));
+    for (int q = 0; q < n_ranks; ++q) h_out[q] = prefix[q];
     return 0;
 }
 
