@@ -300,6 +300,7 @@ def run_b200(a):
         # PCIe roofline denominator, measured in this run: one large pinned H2D copy, best of 3
         probe = min(nbytes, 4 << 30)
         best = None
+        barrier()                                # all ranks probe at the same time: the CONCURRENT per-GPU rate
         for _ in range(3):
             p0 = torch.cuda.Event(enable_timing=True)
             p1 = torch.cuda.Event(enable_timing=True)
