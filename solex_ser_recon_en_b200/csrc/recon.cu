@@ -236,6 +236,136 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
     }
 }
 
+// Column-pair variant: a thread owns two adjacent columns, so one 32-bit shared-memory load
+// brings both taps of a band row and one 32-bit global store writes both outputs (they are
+// adjacent in the frame-major image).  Half the load / store / address instructions per output,
+// and 128-byte instead of 64-byte store requests per warp (matters for peer writes over NVLink).
+__device__ __forceinline__ void st_global_u32(unsigned long long addr, uint32_t v) {
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+template <typename T, int TX, int STAGES, int G>
+__global__ void __launch_bounds__(TX / 2 * G)
+recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ShiftTable tab,
+                      int64_t n_frames, int W, int H, int n_tx, int stage_elems,
+                      const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
+                      const int* __restrict__ row0 /* [n_tx][n_runs] */,
+                      const unsigned long long* __restrict__ out_ptrs, int64_t k0_out) {
+    extern __shared__ unsigned char smem_raw[];
+    T* stage_buf = reinterpret_cast<T*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    __shared__ __align__(8) uint64_t full[STAGES];
+    __shared__ unsigned long long s_out[kMaxShifts];
+    for (int j = threadIdx.x; j < tab.n_shifts; j += blockDim.x) s_out[j] = out_ptrs[j];
+
+    constexpr int HT = TX / 2;
+    const int tid = threadIdx.x;
+    const int cp = tid % HT, grp = tid / HT;
+    const int tx = blockIdx.x % n_tx;
+    const int64_t first = blockIdx.x / n_tx, stride = gridDim.x / n_tx;
+    const uint32_t stage_bytes = (uint32_t)stage_elems * sizeof(T);
+
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t k, int stage) {
+        mbar_expect_tx(&full[stage], stage_bytes);
+        T* dst = stage_buf + (size_t)stage * stage_elems;
+        for (int r = 0; r < tab.n_runs; ++r)
+            tma_load_3d(dst + tab.run_off[r], &maps.m[r], &full[stage], tx * TX, row0[tx * tab.n_runs + r], (int)k, policy);
+    };
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s)
+            if (first + s * stride < n_frames) issue(first + s * stride, s);
+
+    const int iw = H;
+    const int x0 = tx * TX + 2 * cp;                      // columns x0, x0+1 (W is even: both live or neither)
+    const bool live = x0 + 1 < W;
+    const int i1 = W - 2 - x0;                            // output index of column x0+1; column x0 is i1+1
+    int f0 = 0, f1 = 0;
+    double wl0 = 0, wr0 = 0, wl1 = 0, wr1 = 0;
+    if (live) {
+        f0 = fl[i1 + 1]; wl0 = lw[i1 + 1]; wr0 = rw[i1 + 1];
+        f1 = fl[i1];     wl1 = lw[i1];     wr1 = rw[i1];
+    }
+    const bool same = f0 == f1;
+    auto taps = [&](const T* p0, const T* p1, double& a, double& b) {
+        if (same) {
+            if (sizeof(T) == 2) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(p0);
+                a = u32_to_double(w & 0xffffu);
+                b = u32_to_double(w >> 16);
+            } else {
+                const uint32_t w = *reinterpret_cast<const uint16_t*>(p0);
+                a = u32_to_double((w & 0xffu) << 8);
+                b = u32_to_double(w & 0xff00u);
+            }
+        } else {
+            a = px_to_double<T>(p0[0]);
+            b = px_to_double<T>(p1[0]);
+        }
+    };
+    int it = 0;
+    for (int64_t k = first; k < n_frames; k += stride, ++it) {
+        const int stage = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&full[stage], phase);
+        if (live) {
+            const T* buf = stage_buf + (size_t)stage * stage_elems + 2 * cp;
+            const unsigned long long off2 = (unsigned long long)(((k0_out + k) * W + i1) * 2);
+            for (int r = 0; r < tab.n_runs; ++r) {
+                const T* rb = buf + tab.run_off[r];
+                const int base = row0[tx * tab.n_runs + r];
+                const int ja = tab.run_first[r], jb = tab.run_first[r + 1];
+                const int per = (jb - ja + G - 1) / G;
+                const int j0 = ja + grp * per, j1 = min(jb, j0 + per);
+                if (j0 >= j1) continue;
+                const int lo = min(f0, f1) + tab.sh[j0], hi = max(f0, f1) + tab.sh[j1 - 1];
+                if (lo >= 0 && hi <= iw - 2) {
+                    int j = j0;
+                    while (j < j1) {
+                        const int je = min(j1, (int)tab.seg_end[j]);
+                        const T* p0 = rb + (f0 + tab.sh[j] - base) * TX;
+                        const T* p1 = rb + (f1 + tab.sh[j] - base) * TX + 1;
+                        double a, b;
+                        taps(p0, p1, a, b);
+                        double Lw0 = __dmul_rn(a, wl0), Lw1 = __dmul_rn(b, wl1);
+#pragma unroll 4
+                        for (; j < je; ++j) {
+                            p0 += TX;
+                            p1 += TX;
+                            taps(p0, p1, a, b);
+                            const double v0 = __dadd_rn(Lw0, __dmul_rn(a, wr0));
+                            const double v1 = __dadd_rn(Lw1, __dmul_rn(b, wr1));
+                            Lw0 = __dmul_rn(a, wl0);
+                            Lw1 = __dmul_rn(b, wl1);
+                            st_global_u32(s_out[j] + off2,
+                                          (double_floor_to_u32(v1) & 0xffffu) | (double_floor_to_u32(v0) << 16));
+                        }
+                    }
+                } else {
+                    for (int j = j0; j < j1; ++j) {
+                        const int il0 = min(max(f0 + tab.sh[j], 0), iw - 2) - base;
+                        const int il1 = min(max(f1 + tab.sh[j], 0), iw - 2) - base;
+                        const uint32_t q0 = lerp_trunc(px_to_double<T>(rb[il0 * TX]), px_to_double<T>(rb[(il0 + 1) * TX]), wl0, wr0);
+                        const uint32_t q1 = lerp_trunc(px_to_double<T>(rb[il1 * TX + 1]), px_to_double<T>(rb[(il1 + 1) * TX + 1]), wl1, wr1);
+                        st_global_u32(s_out[j] + off2, q1 | (q0 << 16));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t nxt = k + (int64_t)STAGES * stride;
+            if (nxt < n_frames) issue(nxt, stage);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -491,6 +621,40 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
         else if (TX == 128) SHG_DISPATCH_ST(T, 128);             \
         else SHG_DISPATCH_ST(T, 64);                             \
     } while (0)
+    int pair = (W % 2 == 0) ? 1 : 0;                     // column-pair kernel (default); SHG_RECON_PAIR=0 selects the other
+    if (const char* e = getenv("SHG_RECON_PAIR")) pair = pair && atoi(e) != 0;
+    bool all_ptrs_even4 = true;                          // 32-bit stores need 4-byte aligned image bases
+    for (int j = 0; j < n_shifts; ++j) all_ptrs_even4 = all_ptrs_even4 && (optr[j] % 4 == 0);
+    if (pair && all_ptrs_even4 && (TX == 256 || TX == 128)) {
+        const int GP = (G == 2 || G == 4 || G == 8) ? (getenv("SHG_RECON_G") ? G : 4) : 4;
+#define SHG_LAUNCH_PAIR(T, TXV, ST, GV)                                                                    \
+    do {                                                                                                   \
+        auto kern = recon_tma_pair_kernel<T, TXV, ST, GV>;                                                 \
+        SHG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<grid, TXV / 2 * GV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, \
+                                               d_fl, d_lw, d_rw, d_row0, d_optr, k0_out);                  \
+    } while (0)
+#define SHG_PAIR_G(T, TXV, ST)                                   \
+    do {                                                         \
+        if (GP == 2) SHG_LAUNCH_PAIR(T, TXV, ST, 2);             \
+        else if (GP == 8) SHG_LAUNCH_PAIR(T, TXV, ST, 8);        \
+        else SHG_LAUNCH_PAIR(T, TXV, ST, 4);                     \
+    } while (0)
+#define SHG_PAIR_ST(T, TXV)                                      \
+    do {                                                         \
+        if (stages >= 4) SHG_PAIR_G(T, TXV, 4);                  \
+        else SHG_PAIR_G(T, TXV, 3);                              \
+    } while (0)
+#define SHG_PAIR_TX(T)                                           \
+    do {                                                         \
+        if (TX == 256) SHG_PAIR_ST(T, 256);                      \
+        else SHG_PAIR_ST(T, 128);                                \
+    } while (0)
+        if (bytes_per_px == 2) SHG_PAIR_TX(uint16_t);
+        else SHG_PAIR_TX(uint8_t);
+        SHG_LAUNCH_CHECK();
+        return 0;
+    }
     if (bytes_per_px == 2) SHG_DISPATCH_TX(uint16_t);
     else SHG_DISPATCH_TX(uint8_t);
     SHG_LAUNCH_CHECK();
