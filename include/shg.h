@@ -186,22 +186,22 @@ int shg_nms_candidates(const double* d_gi, const double* d_gj, const double* d_m
 int shg_label_points(const int64_t* h_flat, int64_t n, int64_t cols, int32_t* h_labels, int32_t* h_n_labels);
 
 /* ---- a12: transversalium (reference solex_util.py:76-86,383-395,489-516) */
-/* tab[v] = log(v) for v in [0, 65536) (tab[0] = -inf): pixels are uint16, so
- * the reference's log(img[y]/img[y-1]) is tab[a] - tab[b] to ~2e-15 absolute. */
+/* Pixels are uint16, so the reference's log(img[y]/img[y-1]) is taken as L(a) - L(b), where L(v) is
+ * log(v) to ~2e-15 absolute (L(0) = -inf) computed in-kernel.  This entry point tabulates that same
+ * L for v in [0, 65536) (tests, diagnostics); the row statistics do not read a table. */
 int shg_log_table(double* d_tab65536, void* stream);
 /* For each listed row y (rows[j]) of each of n_imgs images (image i at
  * d_img + i*img_stride), over columns [xa[j], xb[j]):
  *   rat = log(img[y][x] / img[y-1][x]);  out[i*n_list + j] = mean(rat[|rat-med|/MAD < 2])
  * (median / MAD as np.median; MAD == 0 keeps all; an empty chord or a nan
  * gives nan as in the reference).  One CTA per (row, image), exact order
- * statistics by radix select in shared memory.  max_len = max(xb-xa).  Chords
+ * statistics (counting select, radix select as fall-back) in shared memory.  max_len = max(xb-xa).  Chords
  * longer than shared memory holds use d_work (shg_transv_workspace_bytes; 0 =
  * not needed). */
 int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs);
 int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
                          const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,
-                         int max_len, const double* d_logtab, double* d_out,
-                         void* d_work, int64_t work_bytes, void* stream);
+                         int max_len, double* d_out, void* d_work, int64_t work_bytes, void* stream);
 /* Gain vectors from the row statistics (reference solex_util.py:400-404,456-479):
  * ratios = [0, stats...] (n values); trend = savgol_filter(ratios, window, 3) with
  * d_coeffs = scipy.signal.savgol_coeffs(window, 3) and cubic end fits; detrended

@@ -58,7 +58,7 @@ _PROTOS = {
     'shg_label_points': (i32, [vp, i64, i64, vp, C.POINTER(C.c_int32)]),
     'shg_log_table': (i32, [vp, vp]),
     'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),
-    'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]),
+    'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, i64, vp]),
     'shg_transv_gain': (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]),
     'shg_row_scale_u16': (i32, [vp, i32, i32, i32, i64, vp, vp, vp]),
     'shg_ingest_create': (i32, [i32, i64, i32, i32, C.POINTER(vp)]),

@@ -9,9 +9,10 @@
 // use a binary radix select over monotone 32-bit keys held bit-sliced in
 // registers (fast_select); longer chords, or rows with very many ties, use a
 // fixed-point 5-bits-per-level select over the value range (block_select).
-// log() comes from a 65536-entry fp64 table: pixels are uint16, so
-// log(a/b) = T[a] - T[b] to ~2e-15 absolute (the reference's own log is only
-// good to ~1e-16 relative of a value that is ~1e-2).
+// Rows whose ratios are all finite (every real scan) take a cheaper route first:
+// a one-level counting select with bin edges from sample quartiles (hist_select).
+// Pixels are uint16, so log(a/b) is taken as L(a) - L(b) with L = log_u16 below
+// (computed, no memory gather), good to ~2e-15 absolute on a quantity of ~1e-2.
 // Stage 2 (shg_row_scale_u16): out = trunc(min(img * gain[row], 65535)).
 // Bound: HBM (each image is read once per stage, written once by stage 2).
 #include <stdlib.h>
@@ -36,6 +37,8 @@ struct Shared {
     int ibc[8];
     double dbc[4];
 };
+
+constexpr int kHistBins = 1024;           // hist_select: one level, lives in Shared::whist (32*33 words)
 
 __device__ __forceinline__ double warp_min(double v) {
     for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -397,12 +400,135 @@ __device__ __forceinline__ bool fast_select(const double* vals, int n, double me
     return true;
 }
 
+// ---------------------------------------------------------------------------
+// First choice for rows whose values are all finite (every real scan): ONE
+// 1024-bin counting pass (shared-memory atomics), a block scan to find the
+// bin(s) that hold ranks t0 <= t1 (t1 - t0 <= 1), and an exact fp64 ranking of
+// the handful of elements in those bins.  The bin index is a monotone
+// non-decreasing function of the key, so every element of a lower bin is <=
+// every element of a higher one and the order statistic is exact whatever the
+// bin edges are.  The edges only decide how many elements share the target bin:
+// they come from the quartiles of a 32-element sample of the row (q_lo, q_hi;
+// limb pixels make min / max useless), 1022 bins over the quartile range widened
+// by 4 IQR each side plus one open bin at each end; for the MAD the keys
+// |rat - med| get 1023 bins over [0, 4 IQR) plus one open bin.
+// ~8 instructions per element and 5 barriers per select (the bit-sliced select
+// below costs ~16 block reductions and a 32x32 bit transpose per 32 elements).
+// Returns false (nothing decided) when the target bins hold more than kListCap
+// elements (heavy duplication, unrepresentative sample): the caller falls back.
+// quartile-ish ranks 8 and 23 of 32 samples of vals[0..n) -> S.dbc[2], S.dbc[3]; warp 0 only, n >= 32
+__device__ __forceinline__ void sample_quartiles(const double* vals, int n, Shared& S) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const double x = vals[(int)(((int64_t)(2 * lane + 1) * n) >> 6)];
+        S.list[lane] = x;
+        __syncwarp();
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double o = S.list[j];
+            rank += (o < x || (o == x && j < lane)) ? 1 : 0;
+        }
+        if (rank == 8) S.dbc[2] = x;
+        if (rank == 23) S.dbc[3] = x;
+    }
+}
+
+template <int KIND, int kT>
+__device__ __forceinline__ bool hist_select(const double* vals, int n, double med, double qlo, double qhi, int t0, int t1,
+                                            Shared& S) {
+    constexpr int BPT = kHistBins / kT;
+    constexpr int NW = kT / 32;
+    static_assert(BPT >= 1 && BPT * kT == kHistBins, "thread count must divide the bin count");
+    unsigned int* H = &S.whist[0][0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b0 = 0, b1 = kHistBins - 1, below = 0, mm = n;
+    // bin = clamp(floor((key - lo) * scale) + first, 0, 1023) through the 1.5*2^52 trick (no conversion pipe);
+    // |(key - lo) * scale| < 2^31 because |key| <= 23 (log ratios of uint16) and iqr >= 1e-5
+    const double iqr = qhi - qlo;
+    const double lo = KIND == 0 ? qlo - 4.0 * iqr : 0.0;
+    const double scale = KIND == 0 ? (double)(kHistBins - 2) / (9.0 * iqr) : (double)(kHistBins - 1) / (4.0 * iqr);
+    const double magic = 6755399441055744.0 + (KIND == 0 ? 1.0 : 0.0);
+    auto bin_of = [&](double x) {
+        const int b = __double2loint(__fma_rd(x - lo, scale, magic));
+        return min(max(b, 0), kHistBins - 1);
+    };
+    if (n > kListCap) {
+        if (!(iqr >= 1e-5)) return false;                     // (uniform across the block)
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) H[q * kT + threadIdx.x] = 0;
+        if (threadIdx.x == 0) S.list_n = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kT) atomicAdd(&H[bin_of(key_of<KIND>(vals, i, med))], 1u);
+        __syncthreads();
+        // exclusive scan over the bins: BPT consecutive bins per thread
+        unsigned int c[BPT], s = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { c[q] = H[threadIdx.x * BPT + q]; s += c[q]; }
+        unsigned int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) S.hist[warp] = inc;
+        __syncthreads();
+        unsigned int exc = inc - s;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) exc += w < warp ? S.hist[w] : 0u;
+        if ((unsigned)t1 >= exc && (unsigned)t0 < exc + s) {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                if (c[q]) {
+                    if ((unsigned)t0 >= exc && (unsigned)t0 < exc + c[q]) { S.ibc[0] = threadIdx.x * BPT + q; S.ibc[1] = (int)exc; }
+                    if ((unsigned)t1 >= exc && (unsigned)t1 < exc + c[q]) { S.ibc[2] = threadIdx.x * BPT + q; S.ibc[3] = (int)(exc + c[q]); }
+                    exc += c[q];
+                }
+            }
+        }
+        __syncthreads();
+        b0 = S.ibc[0]; below = S.ibc[1]; b1 = S.ibc[2];
+        mm = S.ibc[3] - below;                                // bins strictly between b0 and b1 are empty
+        if (mm > kListCap) {
+            __syncthreads();                                  // H (aliases whist) is reused by the caller's fallback
+            return false;
+        }
+        for (int i = threadIdx.x; i < n; i += kT) {
+            const double x = key_of<KIND>(vals, i, med);
+            const int b = bin_of(x);
+            if (b >= b0 && b <= b1) S.list[atomicAdd(&S.list_n, 1)] = x;
+        }
+    } else {
+        // short chord: rank everything
+        for (int i = threadIdx.x; i < n; i += kT) S.list[i] = key_of<KIND>(vals, i, med);
+    }
+    __syncthreads();
+    for (int ci = threadIdx.x; ci < mm; ci += kT) {
+        const double x = S.list[ci];
+        int rank = below;
+        for (int i = 0; i < mm; ++i) {
+            const double o = S.list[i];
+            rank += (o < x || (o == x && i < ci)) ? 1 : 0;
+        }
+        if (rank == t0) S.dbc[0] = x;
+        if (rank == t1) S.dbc[1] = x;
+    }
+    __syncthreads();
+    return true;
+}
+
 // value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
 template <int KIND, int kT>
 __device__ void ranked_pair(const double* vals, int n, double med, int nneg, int nfin,
-                            int t0, int t1, double& v0, double& v1, Shared& S) {
+                            int t0, int t1, double& v0, double& v1, Shared& S, bool hist_ok, double klo, double khi) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
+    if (hist_ok && nfin == n && hist_select<KIND, kT>(vals, n, med, klo, khi, t0, t1, S)) {
+        v0 = S.dbc[0];
+        v1 = S.dbc[1];
+        __syncthreads();
+        return;
+    }
     if (g0 == 0 && g1 == 0) {
         // the common case: both middle ranks are finite values
         constexpr int kWords = kT <= 64 ? 2 : 1;              // 64-thread CTAs own up to 64 elements per thread
@@ -445,16 +571,71 @@ __device__ void ranked_pair(const double* vals, int n, double med, int nneg, int
     }
 }
 
+// ---------------------------------------------------------------------------
+// log(v) for a 16-bit pixel without a memory gather (a 65536-entry fp64 table costs one divergent
+// 8-byte L1 / L2 gather per pixel: the row-statistics kernel spent 2/3 of its time waiting on them).
+//   v = m16 * 2^(e-15), m16 in [2^15, 2^16);  hi = top 7 mantissa bits;  c = fl(1 / (1 + (hi + 1/2)/128))
+//   log(v) = e*ln2 - log(c) + log1p(r),  r = m*c - 1 (one fma: exact to 2^-62), |r| <= 2^-8,
+//   log1p by its degree-6 Taylor polynomial (remainder < 2e-18).  {c / 2^15, -log(c)} come from a
+// 128-entry (2 KB) table staged in shared memory; -log(c) is computed on the host in long double.
+// Absolute error <= ~2e-15 (two roundings at the magnitude of the result, <= 11.1), the same as a table
+// of correctly rounded logs.  v == 0 -> -inf, as np.log(0).
+struct LogSeg { double c, t; };
+static LogSeg g_logseg_host[128];
+__device__ LogSeg g_logseg[128];
+
+static void fill_logseg_host() {
+    static const bool once = [] {                            // thread-safe one-time initialisation
+        for (int h = 0; h < 128; ++h) {
+            const double c = 1.0 / (1.0 + (h + 0.5) / 128.0);
+            g_logseg_host[h].c = c / 32768.0;
+            g_logseg_host[h].t = (double)(-logl((long double)c));
+        }
+        return true;
+    }();
+    (void)once;
+}
+
+__device__ __forceinline__ double log_u16(uint32_t v, const LogSeg* seg /* shared */) {
+    const int e = 31 - __clz((int)v);
+    const uint32_t m16 = v << ((15 - e) & 31);
+    const double2 ct = *reinterpret_cast<const double2*>(&seg[(m16 >> 8) & 127u]);
+    const double r = fma(u32_to_double(m16), ct.x, -1.0);
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    const double ed = u32_to_double((uint32_t)e);
+    const double hi = fma(ed, 6.93147180369123816490e-01, ct.y);       // e * ln2_hi is exact (ln2_hi has 32 bits)
+    const double lo = fma(ed, 1.90821492927058770002e-10, fma(r * r, p, r));
+    return v ? hi + lo : -INFINITY;
+}
+
+constexpr size_t kSharedBytes = (sizeof(Shared) + 15) / 16 * 16;
+constexpr size_t kHeadBytes = kSharedBytes + 128 * sizeof(LogSeg);
+
+__global__ void __launch_bounds__(256)
+log_u16_eval_kernel(double* __restrict__ out) {
+    __shared__ __align__(16) LogSeg seg[128];
+    if (threadIdx.x < 128) seg[threadIdx.x] = g_logseg[threadIdx.x];
+    __syncthreads();
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v < 65536) out[v] = log_u16((uint32_t)v, seg);
+}
+
 template <int kT>
 __global__ void __launch_bounds__(kT, (kT == 64 ? 6 : (kT == 128 ? 6 : (kT == 256 ? 3 : 1))))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
                         const int32_t* __restrict__ xb_list, int n_list,
-                        const double* __restrict__ logtab, double* __restrict__ out,
-                        double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap) {
+                        double* __restrict__ out,
+                        double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap, int use_hist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
-    double* vals = reinterpret_cast<double*>(smem_raw + ((sizeof(Shared) + 15) / 16) * 16);
+    LogSeg* seg = reinterpret_cast<LogSeg*>(smem_raw + kSharedBytes);
+    double* vals = reinterpret_cast<double*>(smem_raw + kHeadBytes);
+    for (int h = threadIdx.x; h < 128; h += kT) seg[h] = g_logseg[h];
+    __syncthreads();
     const int j = blockIdx.x;
     const int64_t slot = (int64_t)blockIdx.y * n_list + j;          // (image, row) result index
     const uint16_t* img = img_base + (int64_t)blockIdx.y * img_stride;
@@ -470,7 +651,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
 
     // ---- rat = log(img[y]/img[y-1]) -------------------------------------------
     unsigned int nnan = 0, nneg = 0, npos = 0;
-    // 8 independent pixel -> log-table chains in flight per thread (the loop is latency-bound otherwise)
+    // 8 independent pixel loads in flight per thread
     for (int i0 = threadIdx.x; i0 < n; i0 += kT * 8) {
         uint16_t pa[8], pb[8];
 #pragma unroll
@@ -479,14 +660,11 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
             pa[u] = i < n ? ry[i] : (uint16_t)1;
             pb[u] = i < n ? rp[i] : (uint16_t)1;
         }
-        double ta[8], tb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { ta[u] = logtab[pa[u]]; tb[u] = logtab[pb[u]]; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kT;
             if (i < n) {
-                const double r = ta[u] - tb[u];
+                const double r = log_u16(pa[u], seg) - log_u16(pb[u], seg);
                 vals[i] = r;
                 if (!(fabs(r) < INFINITY)) {                    // a zero pixel in either row: rare
                     if (r != r) ++nnan;
@@ -517,8 +695,18 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     }
     // ---- median (np.median: mean of the two middle values for even n) ---------
     const int t0 = (n - 1) / 2, t1 = n / 2;
+    // counting select (hist_select): bin edges from the sample quartiles of the row
+    const bool hist_ok = (use_hist & 1) && nfin == n;
+    double qlo = 0.0, qhi = 0.0;
+    if (hist_ok && n > kListCap) {
+        sample_quartiles(vals, n, S);
+        __syncthreads();
+        qlo = S.dbc[2];
+        qhi = S.dbc[3];
+    }
+    if (use_hist & 4) return;                        // diagnostics: cost of the rat phase alone
     double a0, a1;
-    ranked_pair<0, kT>(vals, n, 0.0, t_neg, nfin, t0, t1, a0, a1, S);
+    ranked_pair<0, kT>(vals, n, 0.0, t_neg, nfin, t0, t1, a0, a1, S, hist_ok, qlo, qhi);
     const double med = t0 == t1 ? a0 : (a0 + a1) / 2.0;
     if (!(fabs(med) < INFINITY)) {                   // |rat - med| contains nan -> mean([]) = nan
         if (threadIdx.x == 0) out[slot] = NAN;
@@ -527,7 +715,8 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // ---- MAD -------------------------------------------------------------------
     const int ninf = t_neg + t_pos;
     double b0, b1;
-    ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S);
+    if (use_hist & 8) return;                        // diagnostics: rat phase + median
+    ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S, hist_ok, qlo, qhi);
     const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
     // ---- mean of the inliers ---------------------------------------------------
     double sum = 0.0, cnt = 0.0;
@@ -678,12 +867,6 @@ transv_gain_kernel(const double* __restrict__ stats /* [n_imgs][n-1] */, int n, 
 }
 
 __global__ void __launch_bounds__(256)
-log_table_kernel(double* __restrict__ tab) {
-    const int v = blockIdx.x * 256 + threadIdx.x;
-    if (v < 65536) tab[v] = v == 0 ? -INFINITY : log((double)v);
-}
-
-__global__ void __launch_bounds__(256)
 row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int rows, int cols,
                  const double* __restrict__ gain /* [n_imgs][rows] */, uint16_t* __restrict__ out_base) {
     const int r = blockIdx.y;
@@ -716,7 +899,10 @@ row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int 
 }  // namespace
 
 extern "C" int shg_log_table(double* d_tab65536, void* stream) {
-    log_table_kernel<<<256, 256, 0, as_stream(stream)>>>(d_tab65536);
+    fill_logseg_host();
+    SHG_CHECK(cudaMemcpyToSymbolAsync(g_logseg, g_logseg_host, sizeof(g_logseg_host), 0, cudaMemcpyHostToDevice,
+                                      as_stream(stream)));
+    log_u16_eval_kernel<<<256, 256, 0, as_stream(stream)>>>(d_tab65536);
     SHG_LAUNCH_CHECK();
     return 0;
 }
@@ -733,7 +919,7 @@ static int transv_threads(int max_len) {
 }
 
 static int64_t transv_smem_cap(int optin) {
-    return ((int64_t)optin - (int64_t)((sizeof(Shared) + 15) / 16 * 16)) / 8;
+    return ((int64_t)optin - (int64_t)kHeadBytes) / 8;
 }
 
 extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs) {
@@ -746,8 +932,7 @@ extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_img
 
 extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
                                     const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,
-                                    int max_len, const double* d_logtab, double* d_out, void* d_work,
-                                    int64_t work_bytes, void* stream) {
+                                    int max_len, double* d_out, void* d_work, int64_t work_bytes, void* stream) {
     (void)rows;
     if (n_list <= 0 || n_imgs <= 0) return 0;
     SHG_REQUIRE(max_len >= 0 && max_len <= cols, "shg_transv_row_stats: max_len %d out of range", max_len);
@@ -755,7 +940,7 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     int dev = 0, optin = 0;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int64_t head = (sizeof(Shared) + 15) / 16 * 16;
+    const int64_t head = (int64_t)kHeadBytes;
     const int64_t cap = transv_smem_cap(optin);
     int64_t pitch = 0;
     size_t smem = (size_t)head;
@@ -770,15 +955,19 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     const int smem_cap = max_len <= cap ? max_len : 0;
     const dim3 grid(n_list, n_imgs);
     cudaStream_t st = as_stream(stream);
+    fill_logseg_host();
+    SHG_CHECK(cudaMemcpyToSymbolAsync(g_logseg, g_logseg_host, sizeof(g_logseg_host), 0, cudaMemcpyHostToDevice, st));
 #define SHG_TRANSV_LAUNCH(T)                                                                                        \
     do {                                                                                                            \
         SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                        (int)smem));                                                                 \
         transv_row_stats_kernel<T><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
-                                                          d_logtab, d_out, static_cast<double*>(d_work), pitch,     \
-                                                          smem_cap);                                                \
+                                                          d_out, static_cast<double*>(d_work), pitch, smem_cap,     \
+                                                          use_hist);                                                \
     } while (0)
     const int threads = transv_threads(max_len);
+    int use_hist = 1;                // SHG_TRANSV_HIST=0: bit-sliced select only; +4 / +8: stop after the rat phase / median (timing)
+    if (const char* e = getenv("SHG_TRANSV_HIST")) use_hist = atoi(e);
     if (threads == 64) SHG_TRANSV_LAUNCH(64);
     else if (threads == 128) SHG_TRANSV_LAUNCH(128);
     else if (threads == 256) SHG_TRANSV_LAUNCH(256);

@@ -540,6 +540,7 @@ class Engine:
     # ------------------------------------------------------- transversalium
     @property
     def logtab(self):
+        """L(v) of the row statistics tabulated for v in [0, 65536) (tests / diagnostics only)."""
         if self._logtab is None:
             self._logtab = self.empty((65536,), torch.float64)
             call('shg_log_table', self._logtab.data_ptr(), self.stream)
@@ -579,7 +580,7 @@ class Engine:
         wb = int(lib.shg_transv_workspace_bytes(n, max_len, n_imgs))
         work = self.empty((wb,), torch.uint8) if wb > 0 else None
         call('shg_transv_row_stats', imgs.data_ptr(), h, w, n_imgs, imgs.stride(0), idx[0].data_ptr(),
-             idx[1].data_ptr(), idx[2].data_ptr(), n, max_len, self.logtab.data_ptr(), out.data_ptr(),
+             idx[1].data_ptr(), idx[2].data_ptr(), n, max_len, out.data_ptr(),
              _ptr(work), wb, self.stream)
         self.n_launches += 1
         if device:

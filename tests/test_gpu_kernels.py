@@ -330,6 +330,43 @@ def test_row_stats_lengths_and_duplicates(eng, n):
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13, equal_nan=True)
 
 
+def test_log_u16_matches_numpy(eng):
+    """L(v) used for log(img[y]/img[y-1]) = L(a) - L(b): within 2 ulp of log(v) at the magnitude of the
+    result (the bound derived in transv.cu), -inf at 0 as np.log."""
+    tab = eng.logtab.cpu().numpy()
+    assert tab[0] == -np.inf
+    v = np.arange(1, 65536, dtype=np.float64)
+    assert np.abs(tab[1:] - np.log(v)).max() <= 4e-15
+
+
+@pytest.mark.parametrize('n', [300, 2573, 3277, 9000])
+def test_row_stats_counting_select_equals_bitsliced(eng, n, monkeypatch):
+    """The counting select (sample-quartile bins) and the bit-sliced radix select are two routes to the same
+    exact order statistics: identical bits on noisy rows with limb-like outliers, and against NumPy."""
+    import torch
+    import warnings
+    rng = np.random.default_rng(n)
+    rows_n = 24
+    base = 7500.0 + 2000.0 * np.sin(np.arange(n + 2) / 300.0)
+    img = np.clip(base[None, :] + rng.normal(0.0, 50.0, (rows_n, n + 2)), 1, 65535).astype(np.uint16)
+    img[::2, :40] = 900                                      # a row outside the limb next to one inside: |rat| ~ 2
+    img[1::3, -25:] = 64000
+    img[5, ::7] = img[4, ::7]                                # exact zeros among the ratios
+    d = torch.from_numpy(img).to(eng.device)
+    rows = np.arange(1, rows_n, dtype=np.int32)
+    xa = (np.arange(rows_n - 1) % 3).astype(np.int32)
+    xb = (xa + n - (np.arange(rows_n - 1) % 2)).astype(np.int32)      # odd and even lengths
+    monkeypatch.setenv('SHG_TRANSV_HIST', '1')
+    got = eng.transversalium_row_stats(d, rows, xa, xb)
+    monkeypatch.setenv('SHG_TRANSV_HIST', '0')
+    got0 = eng.transversalium_row_stats(d, rows, xa, xb)
+    assert np.array_equal(got, got0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        want = np.array([_row_stat_ref(img[y, a:b], img[y - 1, a:b]) for y, a, b in zip(rows, xa, xb)])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13, equal_nan=True)
+
+
 def test_row_stats_zeros_inf_nan_empty(eng):
     """Zeros in either row give +-inf / nan exactly as the reference's log(a/b)."""
     import torch
