@@ -416,51 +416,52 @@ __device__ __forceinline__ bool fast_select(const double* vals, int n, double me
 // below costs ~16 block reductions and a 32x32 bit transpose per 32 elements).
 // Returns false (nothing decided) when the target bins hold more than kListCap
 // elements (heavy duplication, unrepresentative sample): the caller falls back.
-// quartile-ish ranks 8 and 23 of 32 samples of vals[0..n) -> S.dbc[2], S.dbc[3]; warp 0 only, n >= 32
-__device__ __forceinline__ void sample_quartiles(const double* vals, int n, Shared& S) {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const double x = vals[(int)(((int64_t)(2 * lane + 1) * n) >> 6)];
-        S.list[lane] = x;
-        __syncwarp();
-        int rank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const double o = S.list[j];
-            rank += (o < x || (o == x && j < lane)) ? 1 : 0;
-        }
-        if (rank == 8) S.dbc[2] = x;
-        if (rank == 23) S.dbc[3] = x;
+// bin = clamp(floor((key - lo) * scale) + first, 0, 1023) through the 1.5*2^52 trick (no conversion pipe);
+// |(key - lo) * scale| < 2^31 because |key| <= 23 (log ratios of uint16) and iqr >= 1e-5
+struct HistBins {
+    double lo, scale, magic;
+    template <int KIND>
+    __device__ __forceinline__ void set(double qlo, double qhi) {
+        const double iqr = qhi - qlo;
+        lo = KIND == 0 ? qlo - 4.0 * iqr : 0.0;
+        scale = KIND == 0 ? (double)(kHistBins - 2) / (9.0 * iqr) : (double)(kHistBins - 1) / (4.0 * iqr);
+        magic = 6755399441055744.0 + (KIND == 0 ? 1.0 : 0.0);
     }
+    __device__ __forceinline__ int operator()(double x) const {
+        const int b = __double2loint(__fma_rd(x - lo, scale, magic));
+        return min(max(b, 0), kHistBins - 1);
+    }
+};
+
+__device__ __forceinline__ bool hist_usable(int n, double qlo, double qhi) {
+    const double iqr = qhi - qlo;
+    return n > kListCap && iqr >= 1e-5 && iqr < 1e30;
 }
 
+// `counted`: the caller has already zeroed H and counted every key into it (the median's
+// counting pass is fused into the loop that computes the ratios).
 template <int KIND, int kT>
 __device__ __forceinline__ bool hist_select(const double* vals, int n, double med, double qlo, double qhi, int t0, int t1,
-                                            Shared& S) {
+                                            bool counted, Shared& S) {
     constexpr int BPT = kHistBins / kT;
     constexpr int NW = kT / 32;
     static_assert(BPT >= 1 && BPT * kT == kHistBins, "thread count must divide the bin count");
     unsigned int* H = &S.whist[0][0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int b0 = 0, b1 = kHistBins - 1, below = 0, mm = n;
-    // bin = clamp(floor((key - lo) * scale) + first, 0, 1023) through the 1.5*2^52 trick (no conversion pipe);
-    // |(key - lo) * scale| < 2^31 because |key| <= 23 (log ratios of uint16) and iqr >= 1e-5
-    const double iqr = qhi - qlo;
-    const double lo = KIND == 0 ? qlo - 4.0 * iqr : 0.0;
-    const double scale = KIND == 0 ? (double)(kHistBins - 2) / (9.0 * iqr) : (double)(kHistBins - 1) / (4.0 * iqr);
-    const double magic = 6755399441055744.0 + (KIND == 0 ? 1.0 : 0.0);
-    auto bin_of = [&](double x) {
-        const int b = __double2loint(__fma_rd(x - lo, scale, magic));
-        return min(max(b, 0), kHistBins - 1);
-    };
+    HistBins bin_of;
+    bin_of.set<KIND>(qlo, qhi);
     if (n > kListCap) {
-        if (!(iqr >= 1e-5)) return false;                     // (uniform across the block)
+        if (!hist_usable(n, qlo, qhi)) return false;          // (uniform across the block)
+        if (!counted) {
 #pragma unroll
-        for (int q = 0; q < BPT; ++q) H[q * kT + threadIdx.x] = 0;
-        if (threadIdx.x == 0) S.list_n = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kT) atomicAdd(&H[bin_of(key_of<KIND>(vals, i, med))], 1u);
-        __syncthreads();
+            for (int q = 0; q < BPT; ++q) H[q * kT + threadIdx.x] = 0;
+            if (threadIdx.x == 0) S.list_n = 0;
+            __syncthreads();
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n; i += kT) atomicAdd(&H[bin_of(key_of<KIND>(vals, i, med))], 1u);
+            __syncthreads();
+        }
         // exclusive scan over the bins: BPT consecutive bins per thread
         unsigned int c[BPT], s = 0;
 #pragma unroll
@@ -493,6 +494,7 @@ __device__ __forceinline__ bool hist_select(const double* vals, int n, double me
             __syncthreads();                                  // H (aliases whist) is reused by the caller's fallback
             return false;
         }
+#pragma unroll 4
         for (int i = threadIdx.x; i < n; i += kT) {
             const double x = key_of<KIND>(vals, i, med);
             const int b = bin_of(x);
@@ -520,10 +522,11 @@ __device__ __forceinline__ bool hist_select(const double* vals, int n, double me
 // value of rank t in the full key set: nneg keys are -inf, then nfin finite keys in [lo, hi], then +inf
 template <int KIND, int kT>
 __device__ void ranked_pair(const double* vals, int n, double med, int nneg, int nfin,
-                            int t0, int t1, double& v0, double& v1, Shared& S, bool hist_ok, double klo, double khi) {
+                            int t0, int t1, double& v0, double& v1, Shared& S, bool hist_ok, double klo, double khi,
+                            bool counted) {
     auto group = [&](int t) { return t < nneg ? -1 : (t < nneg + nfin ? 0 : 1); };
     const int g0 = group(t0), g1 = group(t1);
-    if (hist_ok && nfin == n && hist_select<KIND, kT>(vals, n, med, klo, khi, t0, t1, S)) {
+    if (hist_ok && nfin == n && hist_select<KIND, kT>(vals, n, med, klo, khi, t0, t1, counted, S)) {
         v0 = S.dbc[0];
         v1 = S.dbc[1];
         __syncthreads();
@@ -614,6 +617,36 @@ __device__ __forceinline__ double log_u16(uint32_t v, const LogSeg* seg /* share
 constexpr size_t kSharedBytes = (sizeof(Shared) + 15) / 16 * 16;
 constexpr size_t kHeadBytes = kSharedBytes + 128 * sizeof(LogSeg);
 
+// log(a / b) for two 16-bit pixels.  Neighbouring rows differ by noise, so almost every pair has
+// |z| <= 2^-6 with z = (a - b)/(a + b), where log(a/b) = 2 atanh(z) = 2 (z + z^3/3 + ... + z^9/9)
+// (remainder < 2^-60 relative) costs one reciprocal and five fma -- about half of two log_u16 -- and
+// is good to a few ulp of the RESULT.  Other pairs (limb, zeros) take L(a) - L(b).
+__device__ __forceinline__ bool log_ratio_small(uint32_t a, uint32_t b) {
+    const uint32_t den = a + b;
+    return ((uint32_t)abs((int)a - (int)b) << 6) <= den && den != 0u;
+}
+// the series; only meaningful when log_ratio_small(a, b) (garbage, but no trap, otherwise)
+__device__ __forceinline__ double log_ratio_series(uint32_t a, uint32_t b) {
+    const double dn = u32_to_double(a + b);
+    const double nn = u32_to_double(a + 65536u - b) - 65536.0;
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(dn));           // ~20 bits; den in [1, 131070]
+    double e = fma(-dn, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-dn, x, 1.0);
+    x = fma(x, e, x);
+    const double z = nn * x;
+    const double z2 = z * z;
+    double p = fma(z2, 1.0 / 9.0, 1.0 / 7.0);
+    p = fma(z2, p, 0.2);
+    p = fma(z2, p, 1.0 / 3.0);
+    const double h = fma(z * z2, p, z);
+    return h + h;
+}
+__device__ __forceinline__ double log_ratio_u16(uint32_t a, uint32_t b, const LogSeg* seg) {
+    return log_ratio_small(a, b) ? log_ratio_series(a, b) : log_u16(a, seg) - log_u16(b, seg);
+}
+
 __global__ void __launch_bounds__(256)
 log_u16_eval_kernel(double* __restrict__ out) {
     __shared__ __align__(16) LogSeg seg[128];
@@ -645,32 +678,83 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
         if (threadIdx.x == 0) out[slot] = NAN;
         return;
     }
-    if (n > smem_cap) vals = gscratch + slot * scratch_pitch;
+    if constexpr (kT == 1024) {                     // only chords > 16384 px can exceed shared memory; the other
+        if (n > smem_cap) vals = gscratch + slot * scratch_pitch;   // variants keep a provably-shared pointer (LDS / STS)
+    }
     const uint16_t* ry = img + (int64_t)y * cols + xa;
     const uint16_t* rp = img + (int64_t)(y - 1) * cols + xa;
 
-    // ---- rat = log(img[y]/img[y-1]) -------------------------------------------
-    unsigned int nnan = 0, nneg = 0, npos = 0;
-    // 8 independent pixel loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < n; i0 += kT * 8) {
-        uint16_t pa[8], pb[8];
+    // ---- bin edges of the counting select from 32 sample ratios (warp 0), before the main pass ----
+    const bool want_hist = (use_hist & 1) && n > kListCap;
+    if (want_hist) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const int i = (int)(((int64_t)(2 * lane + 1) * n) >> 6);
+            const double x = log_ratio_u16(ry[i], rp[i], seg);
+            S.list[lane] = x;
+            __syncwarp();
+            int rank = 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kT;
-            pa[u] = i < n ? ry[i] : (uint16_t)1;
-            pb[u] = i < n ? rp[i] : (uint16_t)1;
+            for (int q = 0; q < 32; ++q) {
+                const double o = S.list[q];
+                rank += (o < x || (o == x && q < lane)) ? 1 : 0;
+            }
+            if (rank == 8) S.dbc[2] = x;
+            if (rank == 23) S.dbc[3] = x;
         }
+        unsigned int* H = &S.whist[0][0];
+        for (int q = threadIdx.x; q < kHistBins; q += kT) H[q] = 0;
+        if (threadIdx.x == 0) S.list_n = 0;
+        __syncthreads();
+    }
+    const double qlo = want_hist ? S.dbc[2] : 0.0, qhi = want_hist ? S.dbc[3] : 0.0;
+    const bool counted = want_hist && hist_usable(n, qlo, qhi);     // nan / inf samples -> not usable
+    HistBins bin0;
+    bin0.set<0>(qlo, qhi);
+
+    // ---- rat = log(img[y]/img[y-1]) (+ the counting pass of the median select) -------------------
+    unsigned int nnan = 0, nneg = 0, npos = 0;
+    // U elements per thread and trip: the series of all U are evaluated unconditionally (independent
+    // dependency chains the scheduler can interleave; a branch per element serialised them), the rare
+    // pairs outside its range are redone with two logs; the next trip's pixels are loaded meanwhile.
+    constexpr int U = 4;
+    uint32_t pa[U], pb[U];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kT;
-            if (i < n) {
-                const double r = log_u16(pa[u], seg) - log_u16(pb[u], seg);
-                vals[i] = r;
-                if (!(fabs(r) < INFINITY)) {                    // a zero pixel in either row: rare
-                    if (r != r) ++nnan;
-                    else if (r < 0) ++nneg;
+    for (int u = 0; u < U; ++u) {
+        const int i = (int)threadIdx.x + u * kT;
+        pa[u] = i < n ? ry[i] : 1u;
+        pb[u] = i < n ? rp[i] : 1u;
+    }
+    for (int i0 = threadIdx.x; i0 < n; i0 += kT * U) {
+        uint32_t ca[U], cb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { ca[u] = pa[u]; cb[u] = pb[u]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + (U + u) * kT;
+            pa[u] = i < n ? ry[i] : 1u;
+            pb[u] = i < n ? rp[i] : 1u;
+        }
+        double r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = log_ratio_series(ca[u], cb[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!log_ratio_small(ca[u], cb[u])) {               // limb, dust, zeros
+                r[u] = log_u16(ca[u], seg) - log_u16(cb[u], seg);
+                if (!(fabs(r[u]) < INFINITY) && i0 + u * kT < n) {   // a zero pixel in either row
+                    if (r[u] != r[u]) ++nnan;
+                    else if (r[u] < 0) ++nneg;
                     else ++npos;
                 }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kT;
+            if (i < n) {
+                vals[i] = r[u];
+                if (counted) atomicAdd(&S.whist[0][0] + bin0(r[u]), 1u);
             }
         }
     }
@@ -695,18 +779,11 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     }
     // ---- median (np.median: mean of the two middle values for even n) ---------
     const int t0 = (n - 1) / 2, t1 = n / 2;
-    // counting select (hist_select): bin edges from the sample quartiles of the row
+    // counting select (hist_select) for rows without zeros
     const bool hist_ok = (use_hist & 1) && nfin == n;
-    double qlo = 0.0, qhi = 0.0;
-    if (hist_ok && n > kListCap) {
-        sample_quartiles(vals, n, S);
-        __syncthreads();
-        qlo = S.dbc[2];
-        qhi = S.dbc[3];
-    }
     if (use_hist & 4) return;                        // diagnostics: cost of the rat phase alone
     double a0, a1;
-    ranked_pair<0, kT>(vals, n, 0.0, t_neg, nfin, t0, t1, a0, a1, S, hist_ok, qlo, qhi);
+    ranked_pair<0, kT>(vals, n, 0.0, t_neg, nfin, t0, t1, a0, a1, S, hist_ok, qlo, qhi, counted);
     const double med = t0 == t1 ? a0 : (a0 + a1) / 2.0;
     if (!(fabs(med) < INFINITY)) {                   // |rat - med| contains nan -> mean([]) = nan
         if (threadIdx.x == 0) out[slot] = NAN;
@@ -716,7 +793,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     const int ninf = t_neg + t_pos;
     double b0, b1;
     if (use_hist & 8) return;                        // diagnostics: rat phase + median
-    ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S, hist_ok, qlo, qhi);
+    ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S, hist_ok, qlo, qhi, false);
     const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
     // ---- mean of the inliers ---------------------------------------------------
     double sum = 0.0, cnt = 0.0;
@@ -953,6 +1030,7 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
                     (long long)((int64_t)n_imgs * n_list * pitch * 8));
     }
     const int smem_cap = max_len <= cap ? max_len : 0;
+    SHG_REQUIRE(max_len <= cap || transv_threads(max_len) == 1024, "shg_transv_row_stats: internal: %d px chords", max_len);
     const dim3 grid(n_list, n_imgs);
     cudaStream_t st = as_stream(stream);
     fill_logseg_host();

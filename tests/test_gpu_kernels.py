@@ -339,6 +339,36 @@ def test_log_u16_matches_numpy(eng):
     assert np.abs(tab[1:] - np.log(v)).max() <= 4e-15
 
 
+def test_row_stats_single_pixel_chords_give_log_ratio(eng):
+    """A one-pixel chord returns log(a/b) itself: checks both evaluation routes (the atanh series for
+    near-equal pixels, L(a) - L(b) otherwise) against NumPy."""
+    import torch
+    rng = np.random.default_rng(11)
+    w = 4096
+    img = np.empty((2, w), np.uint16)
+    img[0] = rng.integers(1, 65536, w)
+    near = img[0].astype(np.int64) + rng.integers(-400, 401, w)
+    far = rng.integers(1, 65536, w)
+    img[1] = np.where(np.arange(w) % 2 == 0, np.clip(near, 1, 65535), far)
+    img[1, :8] = img[0, :8]                                   # exact zeros
+    img[0, 8:12] = [1, 65535, 1, 32768]
+    img[1, 8:12] = [65535, 1, 1, 32767]
+    d = torch.from_numpy(img).to(eng.device)
+    xa = np.arange(w, dtype=np.int32)
+    got = eng.transversalium_row_stats(d, np.ones(w, np.int32), xa, xa + 1)
+    a, b = img[1].astype(np.longdouble), img[0].astype(np.longdouble)
+    true = np.log1p((a - b) / b)                              # 80-bit; the reference's own fp64 log(a/b) is ~1e-16 off
+    err = np.abs(got - true).astype(np.float64)
+    z = (np.abs(a - b) / (a + b)).astype(np.float64)
+    small = z <= 2.0 ** -6
+    assert small.sum() > 500 and (~small).sum() > 500
+    assert np.all(err[small] <= 4 * np.spacing(np.abs(got[small])))   # series: a few ulp of the result
+    assert err[~small].max() <= 4e-15                                  # L(a) - L(b): ulps of log(65535)
+    assert np.all(got[:8] == 0.0)
+    ref = np.log(img[1].astype(np.float64) / img[0].astype(np.float64))
+    assert np.abs(got - ref).max() <= 4e-15
+
+
 @pytest.mark.parametrize('n', [300, 2573, 3277, 9000])
 def test_row_stats_counting_select_equals_bitsliced(eng, n, monkeypatch):
     """The counting select (sample-quartile bins) and the bit-sliced radix select are two routes to the same
