@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument('--sample-frames', type=int, default=0, help='CPU arm: frames per step (0 = auto)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--timeline', action='store_true', help='print the stage timeline of one extra resident pass (stderr)')
     ap.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
     return ap.parse_args()
 
@@ -283,6 +284,18 @@ def run_b200(a):
 
     # ---- value: stack resident in HBM
     dev = timed_loop(lambda: device_scan(stack), a.steps, a.warmup, False, 'device')
+
+    if a.timeline and rank == 0:
+        eng.profile_stages = True
+        eng.stage_report()
+        t0 = time.perf_counter()
+        one_pass(device_scan(stack), False)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        for name, s0, s1 in sorted(eng.stage_timeline(), key=lambda t: t[1]):
+            print('timeline %-28s %8.3f -> %8.3f  (%.3f ms)' % (name, s0, s1, s1 - s0), file=sys.stderr)
+        print('timeline wall %.3f ms' % wall, file=sys.stderr)
+        eng.profile_stages = False
 
     # ---- e2e: payload in pinned host memory -> H2D -> ... -> D2H
     e2e = None

@@ -98,12 +98,19 @@ int shg_fit_table(const double* d_coef, int ih, double* d_fit /* ih x 4 */, void
  * owner's image over NVLink -- reconstruction and the row exchange are one
  * kernel.  d_work: device scratch of at least shg_recon_workspace_bytes(ih,
  * n_shifts) bytes.  impl: 0 = auto, 1 = generic direct-load kernel, 2 = TMA
- * band kernel. */
+ * band kernel.
+ * d_min (optional, device uint32[n_shifts], in the order of h_shifts): the kernel
+ * folds min(d_min[s], minimum of the pixels it writes for shift s) into it, so the
+ * caller pre-fills it with 65535 (or the partial minimum of other frame ranges);
+ * the circularisation clips to that minimum (ellipse_to_circle.py:112-118) and
+ * does not have to re-read the images for it.  *h_min_done (optional, HOST) is
+ * set to 1 when the kernel variant that ran maintains d_min, else 0 (the caller
+ * then computes the minimum with shg_minmax_u16). */
 int64_t shg_recon_workspace_bytes(int ih, int n_shifts);
 int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
               const double* h_fit, const int32_t* h_shifts, int n_shifts,
               uint16_t* d_disk, int64_t shift_stride, const uint64_t* h_out_ptrs, int64_t k0_out, int impl,
-              void* d_work, int64_t work_bytes, void* stream);
+              void* d_work, int64_t work_bytes, uint32_t* d_min, int* h_min_done, void* stream);
 
 /* ---- multi-GPU row exchange: device buffers other ranks of the box can write
  * (cudaMalloc + CUDA IPC; handles travel through torch.distributed) -------- */

@@ -38,7 +38,7 @@ _PROTOS = {
     'shg_window_mask': (i32, [vp, i32, dbl, dbl, vp, vp]),
     'shg_fit_table': (i32, [vp, i32, vp, vp]),
     'shg_recon_workspace_bytes': (i64, [i32, i32]),
-    'shg_recon': (i32, [vp, i32, i64, i32, i32, vp, vp, i32, vp, i64, vp, i64, i32, vp, i64, vp]),
+    'shg_recon': (i32, [vp, i32, i64, i32, i32, vp, vp, i32, vp, i64, vp, i64, i32, vp, i64, vp, C.POINTER(C.c_int), vp]),
     'shg_ipc_alloc': (i32, [i64, C.POINTER(vp), C.c_char_p]),
     'shg_ipc_free': (i32, [vp]),
     'shg_ipc_open': (i32, [C.c_char_p, C.POINTER(vp)]),

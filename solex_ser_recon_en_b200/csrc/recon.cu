@@ -250,7 +250,8 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
                       int64_t n_frames, int W, int H, int n_tx, int stage_elems,
                       const int* __restrict__ fl, const double* __restrict__ lw, const double* __restrict__ rw,
                       const int* __restrict__ row0 /* [n_tx][n_runs] */,
-                      const unsigned long long* __restrict__ out_ptrs, int64_t k0_out) {
+                      const unsigned long long* __restrict__ out_ptrs, int64_t k0_out,
+                      uint32_t* __restrict__ gmin /* [n_shifts] by slot, or null */) {
     extern __shared__ unsigned char smem_raw[];
     T* stage_buf = reinterpret_cast<T*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     __shared__ __align__(8) uint64_t full[STAGES];
@@ -258,6 +259,12 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
     for (int j = threadIdx.x; j < tab.n_shifts; j += blockDim.x) s_out[j] = out_ptrs[j];
 
     constexpr int HT = TX / 2;
+    // running minimum of every (shift, column pair) this CTA produces, packed like the stores (the
+    // circularisation clips to the image minimum: folding it in here saves re-reading every image)
+    uint32_t* s_min = reinterpret_cast<uint32_t*>(stage_buf + (size_t)STAGES * stage_elems);
+    const bool do_min = gmin != nullptr;
+    if (do_min)
+        for (int q = threadIdx.x; q < tab.n_shifts * HT; q += blockDim.x) s_min[q] = 0xFFFFFFFFu;
     const int tid = threadIdx.x;
     const int cp = tid % HT, grp = tid / HT;
     const int tx = blockIdx.x % n_tx;
@@ -343,8 +350,12 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
                             const double v1 = __dadd_rn(Lw1, __dmul_rn(b, wr1));
                             Lw0 = __dmul_rn(a, wl0);
                             Lw1 = __dmul_rn(b, wl1);
-                            st_global_u32(s_out[j] + off2,
-                                          (double_floor_to_u32(v1) & 0xffffu) | (double_floor_to_u32(v0) << 16));
+                            const uint32_t w = (double_floor_to_u32(v1) & 0xffffu) | (double_floor_to_u32(v0) << 16);
+                            st_global_u32(s_out[j] + off2, w);
+                            if (do_min) {
+                                uint32_t* m = s_min + j * HT + cp;
+                                *m = __vminu2(*m, w);
+                            }
                         }
                     }
                 } else {
@@ -354,6 +365,10 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
                         const uint32_t q0 = lerp_trunc(px_to_double<T>(rb[il0 * TX]), px_to_double<T>(rb[(il0 + 1) * TX]), wl0, wr0);
                         const uint32_t q1 = lerp_trunc(px_to_double<T>(rb[il1 * TX + 1]), px_to_double<T>(rb[(il1 + 1) * TX + 1]), wl1, wr1);
                         st_global_u32(s_out[j] + off2, q1 | (q0 << 16));
+                        if (do_min) {
+                            uint32_t* m = s_min + j * HT + cp;
+                            *m = __vminu2(*m, q1 | (q0 << 16));
+                        }
                     }
                 }
             }
@@ -362,6 +377,16 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
         if (tid == 0) {
             const int64_t nxt = k + (int64_t)STAGES * stride;
             if (nxt < n_frames) issue(nxt, stage);
+        }
+    }
+    if (do_min) {                                         // (the loop ends with a barrier: the table is complete)
+        const int lane = tid & 31, nw = (HT * G) >> 5;
+        for (int j = tid >> 5; j < tab.n_shifts; j += nw) {
+            uint32_t v = 0xFFFFFFFFu;
+            for (int q = lane; q < HT; q += 32) v = __vminu2(v, s_min[j * HT + q]);
+            v = min(v & 0xffffu, v >> 16);
+            v = __reduce_min_sync(0xffffffffu, v);
+            if (lane == 0) atomicMin(&gmin[tab.slot[j]], v);
         }
     }
 }
@@ -448,7 +473,8 @@ extern "C" int64_t shg_recon_workspace_bytes(int ih, int n_shifts) {
 extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
                          const double* h_fit, const int32_t* h_shifts, int n_shifts,
                          uint16_t* d_disk, int64_t shift_stride, const uint64_t* h_out_ptrs, int64_t k0_out,
-                         int impl, void* d_work, int64_t work_bytes, void* stream) {
+                         int impl, void* d_work, int64_t work_bytes, uint32_t* d_min, int* h_min_done, void* stream) {
+    if (h_min_done) *h_min_done = 0;
     SHG_REQUIRE(bytes_per_px == 1 || bytes_per_px == 2, "shg_recon: bytes_per_px must be 1 or 2");
     SHG_REQUIRE(n_shifts >= 1 && n_shifts <= kMaxShifts, "shg_recon: %d shifts (max %d)", n_shifts, kMaxShifts);
     SHG_REQUIRE(W >= 2 && H >= 2, "shg_recon: bad geometry %dx%d", W, H);
@@ -586,7 +612,22 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     int dev = 0, sms = SHG_SM_COUNT_B200;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = (size_t)plan.stage_elems * bytes_per_px * stages + 128;
+    size_t smem = (size_t)plan.stage_elems * bytes_per_px * stages + 128;
+    int pair = (W % 2 == 0) ? 1 : 0;                     // column-pair kernel (default); SHG_RECON_PAIR=0 selects the other
+    if (const char* e = getenv("SHG_RECON_PAIR")) pair = pair && atoi(e) != 0;
+    bool all_ptrs_even4 = true;                          // 32-bit stores need 4-byte aligned image bases
+    for (int j = 0; j < n_shifts; ++j) all_ptrs_even4 = all_ptrs_even4 && (optr[j] % 4 == 0);
+    const bool use_pair = pair && all_ptrs_even4 && (TX == 256 || TX == 128);
+    // per-image minimum folded into the pair kernel when its (shift x column pair) table fits beside the stages
+    uint32_t* gmin = nullptr;
+    if (use_pair && d_min && !getenv("SHG_RECON_NO_MIN")) {
+        const size_t min_bytes = (size_t)n_shifts * (TX / 2) * 4;
+        if (smem + min_bytes + 6 * 1024 <= 227 * 1024) {
+            gmin = d_min;
+            smem += min_bytes;
+            if (h_min_done) *h_min_done = 1;
+        }
+    }
     const int64_t n_tiles = n_frames * plan.n_tx;
     const int by_smem = std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const int by_threads = std::max(1, 2048 / (TX * G));
@@ -621,18 +662,14 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
         else if (TX == 128) SHG_DISPATCH_ST(T, 128);             \
         else SHG_DISPATCH_ST(T, 64);                             \
     } while (0)
-    int pair = (W % 2 == 0) ? 1 : 0;                     // column-pair kernel (default); SHG_RECON_PAIR=0 selects the other
-    if (const char* e = getenv("SHG_RECON_PAIR")) pair = pair && atoi(e) != 0;
-    bool all_ptrs_even4 = true;                          // 32-bit stores need 4-byte aligned image bases
-    for (int j = 0; j < n_shifts; ++j) all_ptrs_even4 = all_ptrs_even4 && (optr[j] % 4 == 0);
-    if (pair && all_ptrs_even4 && (TX == 256 || TX == 128)) {
+    if (use_pair) {
         const int GP = (G == 2 || G == 4 || G == 8) ? (getenv("SHG_RECON_G") ? G : 4) : 4;
 #define SHG_LAUNCH_PAIR(T, TXV, ST, GV)                                                                    \
     do {                                                                                                   \
         auto kern = recon_tma_pair_kernel<T, TXV, ST, GV>;                                                 \
         SHG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         kern<<<grid, TXV / 2 * GV, smem, st>>>(maps, plan.tab, n_frames, W, H, plan.n_tx, plan.stage_elems, \
-                                               d_fl, d_lw, d_rw, d_row0, d_optr, k0_out);                  \
+                                               d_fl, d_lw, d_rw, d_row0, d_optr, k0_out, gmin);            \
     } while (0)
 #define SHG_PAIR_G(T, TXV, ST)                                   \
     do {                                                         \

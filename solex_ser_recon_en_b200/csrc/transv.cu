@@ -464,8 +464,18 @@ __device__ __forceinline__ bool hist_select(const double* vals, int n, double me
         }
         // exclusive scan over the bins: BPT consecutive bins per thread
         unsigned int c[BPT], s = 0;
+        if constexpr (BPT % 4 == 0) {
 #pragma unroll
-        for (int q = 0; q < BPT; ++q) { c[q] = H[threadIdx.x * BPT + q]; s += c[q]; }
+            for (int q = 0; q < BPT; q += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(H + threadIdx.x * BPT + q);
+                c[q] = v.x; c[q + 1] = v.y; c[q + 2] = v.z; c[q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) c[q] = H[threadIdx.x * BPT + q];
+        }
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) s += c[q];
         unsigned int inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -656,7 +666,7 @@ log_u16_eval_kernel(double* __restrict__ out) {
     if (v < 65536) out[v] = log_u16((uint32_t)v, seg);
 }
 
-template <int kT>
+template <int kT, int U>
 __global__ void __launch_bounds__(kT, (kT == 64 ? 6 : (kT == 128 ? 6 : (kT == 256 ? 3 : 1))))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
@@ -717,7 +727,6 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // U elements per thread and trip: the series of all U are evaluated unconditionally (independent
     // dependency chains the scheduler can interleave; a branch per element serialised them), the rare
     // pairs outside its range are redone with two logs; the next trip's pixels are loaded meanwhile.
-    constexpr int U = 4;
     uint32_t pa[U], pb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -796,21 +805,30 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     ranked_pair<1, kT>(vals, n, med, 0, n - ninf, t0, t1, b0, b1, S, hist_ok, qlo, qhi, false);
     const double mdev = t0 == t1 ? b0 : (b0 + b1) / 2.0;
     // ---- mean of the inliers ---------------------------------------------------
-    double sum = 0.0, cnt = 0.0;
+    double sum = 0.0;
+    int kept = 0;
     if (mdev != 0.0) {                               // (nan is truthy in the reference too, but cannot occur here)
         // fl(d / mdev) < 2  <=>  d < 2*mdev for positive normal doubles (2*mdev is exact, and the largest
         // double below it divides to at most 2 - 2^-52), so the per-element division is not needed
         const double thr = 2.0 * mdev;
-        const bool exact = mdev > 1e-300 && mdev < 1e300;
-        for (int i = threadIdx.x; i < n; i += kT) {
-            const double r = vals[i];
-            const double d = fabs(r - med);
-            const bool keep = exact ? (d < thr) : (d / mdev < 2.0);
-            if (keep) { sum += r; cnt += 1.0; }
+        if (mdev > 1e-300 && mdev < 1e300) {
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n; i += kT) {
+                const double r = vals[i];
+                const bool keep = fabs(r - med) < thr;
+                sum += keep ? r : 0.0;
+                kept += keep ? 1 : 0;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += kT) {
+                const double r = vals[i];
+                if (fabs(r - med) / mdev < 2.0) { sum += r; ++kept; }
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < n; i += kT) { sum += vals[i]; cnt += 1.0; }
+        for (int i = threadIdx.x; i < n; i += kT) { sum += vals[i]; ++kept; }
     }
+    double cnt = (double)kept;
     block_sum2(sum, cnt, S);
     if (threadIdx.x == 0) out[slot] = sum / cnt;
 }
@@ -1037,16 +1055,22 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     SHG_CHECK(cudaMemcpyToSymbolAsync(g_logseg, g_logseg_host, sizeof(g_logseg_host), 0, cudaMemcpyHostToDevice, st));
 #define SHG_TRANSV_LAUNCH(T)                                                                                        \
     do {                                                                                                            \
-        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                        (int)smem));                                                                 \
-        transv_row_stats_kernel<T><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
+        transv_row_stats_kernel<T, 4><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
                                                           d_out, static_cast<double*>(d_work), pitch, smem_cap,     \
                                                           use_hist);                                                \
     } while (0)
     const int threads = transv_threads(max_len);
     int use_hist = 1;                // SHG_TRANSV_HIST=0: bit-sliced select only; +4 / +8: stop after the rat phase / median (timing)
     if (const char* e = getenv("SHG_TRANSV_HIST")) use_hist = atoi(e);
-    if (threads == 64) SHG_TRANSV_LAUNCH(64);
+    if (threads == 128 && getenv("SHG_TRANSV_U8")) {         // tuning: 8 interleaved chains per thread
+        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        transv_row_stats_kernel<128, 8><<<grid, 128, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,
+                                                                 d_out, static_cast<double*>(d_work), pitch, smem_cap,
+                                                                 use_hist);
+    } else if (threads == 64) SHG_TRANSV_LAUNCH(64);
     else if (threads == 128) SHG_TRANSV_LAUNCH(128);
     else if (threads == 256) SHG_TRANSV_LAUNCH(256);
     else if (threads == 512) SHG_TRANSV_LAUNCH(512);

@@ -27,6 +27,7 @@ class DeviceImage:
         self._host = None
         self._rows = None
         self.fit_future = None        # limb search started early on this image (solex_util.read_video_improved)
+        self.min_ref = None           # (int32 device tensor, index): minimum pixel, tracked by the reconstruction
 
     # ---- array protocol -----------------------------------------------------
     @property
@@ -76,6 +77,7 @@ class DeviceImage:
         if self.layout == 'frames':
             out = DeviceImage(self.engine, self.tensor, 'frames', not self.flip)
             out.fit_future = self.fit_future      # the early fit was started on the image as it will be used
+            out.min_ref = self.min_ref
             return out
         return np.flip(self.numpy(), axis=1)
 

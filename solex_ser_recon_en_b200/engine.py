@@ -164,6 +164,17 @@ class Engine:
         self._stage_events = []
         return out
 
+    def stage_timeline(self):
+        """[(name, start_ms, end_ms)] of the recorded stages relative to the first one (diagnostics:
+        which stages overlap, where the device idles).  Clears the record like stage_report()."""
+        torch.cuda.synchronize(self.device)
+        ev = getattr(self, '_stage_events', [])
+        self._stage_events = []
+        if not ev:
+            return []
+        base = ev[0][1]
+        return [(name, base.elapsed_time(a), base.elapsed_time(b)) for name, a, b in ev]
+
     @property
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -362,25 +373,32 @@ class Engine:
         return self.empty((n_shifts, n_frames, ih), torch.uint16)
 
     def recon(self, stack: DeviceStack, fit: np.ndarray, shifts, disk=None, k0_out: int | None = None,
-              impl: int = 0, out_ptrs=None):
+              impl: int = 0, out_ptrs=None, mins=None):
         """disk[s, k, i] (frame-major) for the frames of `stack`; with `disk`
         given the rows land at frame offset k0_out (default: the stack's k0).
         `out_ptrs` (one device address per shift, possibly on peer GPUs) replaces
-        `disk`: each shift's rows are written into that image at offset k0_out."""
+        `disk`: each shift's rows are written into that image at offset k0_out.
+        `mins` (int32 device tensor, one per shift, pre-filled with 65535 or a partial
+        minimum): the kernel folds the minimum of what it writes into it;
+        self.recon_min_done tells whether the variant that ran does so."""
         g = stack.geom
         shifts = np.ascontiguousarray(shifts, dtype=np.int32)
         fit = np.ascontiguousarray(fit, dtype=np.float64)
         assert fit.shape == (g.ih, 4)
+        assert mins is None or (mins.numel() == len(shifts) and mins.dtype == torch.int32 and mins.is_contiguous())
+        done = C.c_int(0)
+        wb = int(lib.shg_recon_workspace_bytes(g.ih, len(shifts)))
+        if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
+            self._recon_ws = self.empty((wb,), torch.uint8)
         if out_ptrs is not None:
             ptrs = np.ascontiguousarray(out_ptrs, dtype=np.uint64)
             assert len(ptrs) == len(shifts)
-            wb = int(lib.shg_recon_workspace_bytes(g.ih, len(shifts)))
-            if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
-                self._recon_ws = self.empty((wb,), torch.uint8)
             call('shg_recon', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.width, g.height,
                  fit.ctypes.data, shifts.ctypes.data, len(shifts), 0, 0, ptrs.ctypes.data,
-                 int(stack.k0 if k0_out is None else k0_out), int(impl), self._recon_ws.data_ptr(), wb, self.stream)
+                 int(stack.k0 if k0_out is None else k0_out), int(impl), self._recon_ws.data_ptr(), wb,
+                 _ptr(mins), C.byref(done), self.stream)
             self.n_launches += 1
+            self.recon_min_done = bool(done.value)
             return None
         if disk is None:
             disk = self.alloc_disk(len(shifts), stack.n, g.ih)
@@ -388,13 +406,11 @@ class Engine:
         elif k0_out is None:
             k0_out = stack.k0
         assert disk.shape[0] == len(shifts) and disk.shape[2] == g.ih and disk.is_contiguous()
-        wb = int(lib.shg_recon_workspace_bytes(g.ih, len(shifts)))
-        if getattr(self, '_recon_ws', None) is None or self._recon_ws.numel() < wb:
-            self._recon_ws = self.empty((wb,), torch.uint8)
         call('shg_recon', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.width, g.height,
              fit.ctypes.data, shifts.ctypes.data, len(shifts), disk.data_ptr(), disk.stride(0), 0, int(k0_out),
-             int(impl), self._recon_ws.data_ptr(), wb, self.stream)
+             int(impl), self._recon_ws.data_ptr(), wb, _ptr(mins), C.byref(done), self.stream)
         self.n_launches += 1
+        self.recon_min_done = bool(done.value)
         return disk
 
     def to_reference_layout(self, disk_s, flip: bool = False):

@@ -177,9 +177,12 @@ def gather_rows(local_disk, n_frames: int, dst: int = 0):
 
 
 def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
-    """Reconstruct this rank's frames at every shift.  Returns a list with one
-    frame-major (N, ih) device image per shift -- every image on a single GPU;
-    with several ranks, the images this rank owns and None for the others.
+    """Reconstruct this rank's frames at every shift.  Returns (images, mins, known):
+    `images` has one frame-major (N, ih) device image per shift -- every image on a
+    single GPU; with several ranks, the images this rank owns and None for the others.
+    `mins` is an int32 device tensor with the minimum pixel of every image the
+    reconstruction kernel tracked (`known[j]`; all ranks' rows included): the
+    circularisation clips to it and does not need a pass over the images for it.
 
     `first_done(image0, ready_event)` (optional) is called once the image of shifts[0]
     -- the ellipse-fit shift -- is complete (on its owner, rank 0), while the
@@ -189,6 +192,8 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     rank, size = world()
     n_s = len(shifts)
     split = first_done is not None and n_s > 1
+    mins = torch.full((n_s,), 65535, dtype=torch.int32, device=eng.device)
+    known = [False] * n_s
     if size == 1:
         disk = eng.alloc_disk(n_s, stack.n, stack.geom.ih)
         if split:
@@ -198,11 +203,13 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
             ready.record()
             # queue the big kernel BEFORE waking the helper thread: the helper's Python work would otherwise
             # hold the interpreter lock while this thread still has the launch to do
-            eng.recon(stack, fit, shifts[1:], disk=disk[1:], k0_out=0)
+            eng.recon(stack, fit, shifts[1:], disk=disk[1:], k0_out=0, mins=mins[1:])
+            known[1:] = [eng.recon_min_done] * (n_s - 1)
             first_done(disk[0], ready)
         else:
-            eng.recon(stack, fit, shifts, disk=disk, k0_out=0)
-        return [disk[i] for i in range(n_s)]
+            eng.recon(stack, fit, shifts, disk=disk, k0_out=0, mins=mins)
+            known = [eng.recon_min_done] * n_s
+        return [disk[i] for i in range(n_s)], mins, known
     g = stack.geom
     ex = row_exchange(n_s, g.n_frames, g.ih)
     torch.cuda.synchronize()
@@ -211,17 +218,21 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
         eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0, impl=1)
         torch.cuda.synchronize()
         dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
-        eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0)
+        eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0, mins=mins[1:])
+        known[1:] = [eng.recon_min_done] * (n_s - 1)
         if ex.owner[0] == rank:
             first_done(ex.images[0], None)             # image 0 is complete (barrier above)
     else:
-        eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0)
+        eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0, mins=mins)
+        known = [eng.recon_min_done] * n_s
+    # every rank tracked the minimum of its own frame rows (same kernel variant everywhere: same geometry)
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()
     dist.barrier()                         # every rank's rows have landed
     out = [None] * n_s
     for n, j in enumerate(ex.mine):
         out[j] = ex.images[n]
-    return out
+    return out, mins, known
 
 
 def broadcast_object(obj, src: int):

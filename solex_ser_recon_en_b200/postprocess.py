@@ -63,10 +63,35 @@ def start_minmax(images):
     side = eng._side_stream
     side.wait_stream(torch.cuda.current_stream(eng.device))
     with torch.cuda.stream(side):
-        mm = eng.minmax_device(base, idx)
+        with eng.stage('minmax'):
+            mm = _minmax_with_tracked(eng, images, base, idx)
     done = torch.cuda.Event()
     done.record(side)
     return dict(ptrs=[p[0].data_ptr() for p in pairs], base=base, idx=idx, mm=mm, done=done)
+
+
+def _minmax_with_tracked(eng, images, base, idx):
+    """(n, 2) int32 clip range of every image.  The reconstruction kernel tracks the minimum of the
+    images it writes (DeviceImage.min_ref) and only the LOWER clip can change a truncated pixel (see
+    csrc/warp.cu), so tracked images get (min, 65535) without touching their pixels; the others (the
+    ellipse-fit shift, reconstructed by the direct-load kernel) go through the min / max kernel."""
+    refs = [getattr(im, 'min_ref', None) for im in images]
+    unknown = [n for n, r in enumerate(refs) if r is None]
+    if len(unknown) == len(images):
+        return eng.minmax_device(base, idx)
+    mm = torch.empty((len(images), 2), dtype=torch.int32, device=eng.device)
+    mm[:, 1] = 65535
+    by_tensor = {}
+    for n, r in enumerate(refs):
+        if r is not None:
+            by_tensor.setdefault(id(r[0]), (r[0], [], []))
+            by_tensor[id(r[0])][1].append(n)
+            by_tensor[id(r[0])][2].append(r[1])
+    for mins, pos, src in by_tensor.values():
+        mm[torch.tensor(pos, device=eng.device), 0] = mins[torch.tensor(src, device=eng.device)]
+    if unknown:
+        mm[torch.tensor(unknown, device=eng.device)] = eng.minmax_device(base, [idx[n] for n in unknown])
+    return mm
 
 
 def circularise_many(images, phi, ratio, prepared=None):

@@ -270,9 +270,12 @@ def read_video_improved(rdr, fit, options):
             from .ellipse_to_circle import start_fit
             prefetch['fit'] = start_fit(DeviceImage(eng, image0, 'frames', bool(options.get('flip_x'))), ready)
     with eng.stage('recon+gather'):
-        disk = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
+        disk, mins, known = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
     # one image per shift; under several ranks only the images this rank owns (None elsewhere)
     disk_list = [None if d is None else DeviceImage(eng, d, 'frames') for d in disk]
+    for j, im in enumerate(disk_list):
+        if im is not None and known[j]:
+            im.min_ref = (mins, j)                               # the kernel tracked this image's minimum
     if 'fit' in prefetch and disk_list[0] is not None:
         disk_list[0].fit_future = prefetch['fit']
     if options['flag_display'] and disk_list[1] is not None:

@@ -178,6 +178,32 @@ def test_recon_sparse_shift_list(eng):
             assert np.array_equal(u16(disk[i]).T, ref[i]), (impl, shifts[i])
 
 
+@pytest.mark.parametrize('name', ['ser16_rot', 'ser8_rot_flip'])
+def test_recon_tracks_image_minimum(eng, name):
+    """The TMA kernel folds min(pixels it writes) of every shift into `mins` (the circularisation's
+    lower clip): equal to the minimum of the image, including clipped shifts, and accumulating over
+    frame ranges like ranks do."""
+    import torch
+    _, stack = case_stack(name)
+    g = golden(name)
+    shifts = O.shift_list(list(range(-50, 51)))
+    n = stack.shape[0]
+    disk = eng.alloc_disk(len(shifts), n, stack.shape[2])
+    mins = torch.full((len(shifts),), 65535, dtype=torch.int32, device=eng.device)
+    for k0, k1 in ((0, 47), (47, n)):
+        st = eng.ingest_array(stack[k0:k1], n_total=n, k0=k0, accumulate=False)
+        eng.recon(st, g['fit'], shifts, disk=disk, mins=mins)
+        assert eng.recon_min_done
+    want = u16(disk).reshape(len(shifts), -1).min(axis=1).astype(np.int64)
+    assert np.array_equal(mins.cpu().numpy(), want)
+    ref = O.recon(stack, g['fit'], shifts)
+    assert mins.cpu().tolist() == [int(r.min()) for r in ref]
+    # the direct-load kernel does not track it and says so
+    st = eng.ingest_array(stack, accumulate=False)
+    eng.recon(st, g['fit'], shifts[:2], impl=1, mins=mins[:2].clone())
+    assert not eng.recon_min_done
+
+
 def test_recon_frame_ranges_tile_the_output(eng):
     """Rank-style sharding: two stacks of frame ranges write disjoint frame rows of one disk."""
     _, stack = case_stack('ser16_rot')

@@ -93,7 +93,8 @@ def main():
     nb = max(shifts) - min(shifts) + 2
     recon_bytes = a.frames * (geom.ih * nb * a.bpp + len(shifts) * geom.ih * 2)
     if want('recon'):
-        ms, best = timed(lambda: eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0, impl=a.impl), a.reps)
+        mins = torch.full((len(shifts),), 65535, dtype=torch.int32, device=eng.device)   # tracked image minima
+        ms, best = timed(lambda: eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0, impl=a.impl, mins=mins), a.reps)
         res['recon'] = dict(ms=ms, best_ms=best, GBps=recon_bytes / ms / 1e6, n_shifts=len(shifts), nb=nb)
     eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0)
     img_bytes = a.frames * geom.ih * 2
