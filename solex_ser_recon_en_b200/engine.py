@@ -128,6 +128,21 @@ class _Stage:
         return False
 
 
+class _EarlyDownload:
+    def __init__(self, eng, t, ev):
+        self.eng, self.t, self.ev = eng, t, ev
+
+    def result(self) -> np.ndarray:
+        up = self.eng._upload_stream
+        up.wait_event(self.ev)
+        with torch.cuda.stream(up):
+            host = torch.empty(self.t.shape, dtype=self.t.dtype, pin_memory=True)
+            host.copy_(self.t, non_blocking=True)
+        self.t.record_stream(up)
+        up.synchronize()
+        return host.numpy()
+
+
 class Engine:
     """One per process / GPU."""
 
@@ -182,10 +197,35 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def upload(self, arr) -> torch.Tensor:
+        """Small host array -> device tensor without waiting for the work queued on the
+        current stream.  torch.tensor(..., device=...) / .to(device) from pageable memory
+        synchronise the stream they copy on; index lists and chord tables uploaded that
+        way held the host until the kernel in front of them had finished, and every
+        launch behind them started late.  Here the copy runs on a stream of its own."""
+        if not hasattr(self, '_upload_stream'):
+            self._upload_stream = torch.cuda.Stream(device=self.device)
+        host = torch.from_numpy(np.ascontiguousarray(arr))
+        with torch.cuda.stream(self._upload_stream):
+            t = host.to(self.device)                    # synchronises the upload stream only
+        t.record_stream(torch.cuda.current_stream(self.device))
+        return t
+
     def sync(self):
         torch.cuda.synchronize(self.device)
 
     # ---------------------------------------------------------------- ingest
+    def download_early(self, t: torch.Tensor) -> np.ndarray:
+        """Host copy of a device tensor that is complete on the current stream NOW, without
+        waiting for kernels queued after this call: the copy runs on the upload stream
+        behind an event recorded here.  Call it right after the producer and before
+        launching the next stage; the result is read with .result()."""
+        if not hasattr(self, '_upload_stream'):
+            self._upload_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return _EarlyDownload(self, t, ev)
+
     def pinned_alloc(self, nbytes: int) -> int:
         """Exact-size pinned host buffer (freed with pinned_free)."""
         p = C.c_void_p()
@@ -428,7 +468,7 @@ class Engine:
             imgs = imgs.unsqueeze(0)
         assert imgs.is_contiguous()
         n_imgs = imgs.shape[0] if sel is None else len(sel)
-        sel_t = None if sel is None else torch.tensor(list(sel), dtype=torch.int32, device=self.device)
+        sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
         mm = self.empty((n_imgs, 2), torch.int32)
         call('shg_minmax_u16', imgs.data_ptr(), imgs[0].numel(), imgs.stride(0), _ptr(sel_t), n_imgs,
              mm.data_ptr(), self.stream)
@@ -451,7 +491,7 @@ class Engine:
                 mat3[2, 0] == 0 and mat3[2, 1] == 0 and mat3[2, 2] == 1):
             raise ShgError('warp matrix is not the row-preserving form get_correction_matrix produces')
         n_imgs = disks.shape[0] if sel is None else len(sel)
-        sel_t = None if sel is None else torch.tensor(list(sel), dtype=torch.int32, device=self.device)
+        sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
         if minmax_dev is None:
             minmax_dev = self.minmax_device(disks, sel)
         oh, ow = int(out_shape[0]), int(out_shape[1])
@@ -468,7 +508,7 @@ class Engine:
         default to the image's min / max (what skimage's warp clips to)."""
         mm = None
         if lo is not None and hi is not None:
-            mm = torch.tensor([[int(lo), int(hi)]], dtype=torch.int32, device=self.device)
+            mm = self.upload(np.array([[int(lo), int(hi)]], dtype=np.int32))
         res = self.warp_batch(disk_s, None, flip, mat3, out_shape, mm,
                               None if out is None else out.unsqueeze(0))
         return res[0]
@@ -590,7 +630,7 @@ class Engine:
         assert imgs.stride(1) == w and imgs.stride(2) == 1
         if rows.min() < 1 or rows.max() >= h or xa.min() < 0 or xb.max() > w:
             raise IndexError('transversalium chord outside the image')     # the reference would raise / wrap too
-        idx = torch.from_numpy(np.stack([rows, xa, xb]).astype(np.int32)).to(self.device)
+        idx = self.upload(np.stack([rows, xa, xb]).astype(np.int32))
         out = self.empty((n_imgs, n), torch.float64)
         max_len = int(max(0, (xb - xa).max()))
         wb = int(lib.shg_transv_workspace_bytes(n, max_len, n_imgs))
@@ -616,7 +656,7 @@ class Engine:
         key = (n, window)
         if getattr(self, '_gain_tab_key', None) != key:
             tab = np.concatenate([savgol_coeffs(window, 3), tukey_taper(n)])
-            self._gain_tab = torch.from_numpy(tab).to(self.device)
+            self._gain_tab = self.upload(tab)
             self._gain_tab_key = key
         n_imgs = stats_dev.shape[0]
         assert stats_dev.shape[1] == n - 1 and stats_dev.is_contiguous()
@@ -635,7 +675,7 @@ class Engine:
         n_imgs, h, w = imgs.shape
         assert imgs.stride(1) == w and imgs.stride(2) == 1
         g = gain if isinstance(gain, torch.Tensor) else \
-            torch.from_numpy(np.ascontiguousarray(gain, dtype=np.float64)).to(self.device)
+            self.upload(np.ascontiguousarray(gain, dtype=np.float64))
         assert g.numel() == n_imgs * h
         if out is None:
             out = self.empty((n_imgs, h, w), torch.uint16)

@@ -88,9 +88,9 @@ def _minmax_with_tracked(eng, images, base, idx):
             by_tensor[id(r[0])][1].append(n)
             by_tensor[id(r[0])][2].append(r[1])
     for mins, pos, src in by_tensor.values():
-        mm[torch.tensor(pos, device=eng.device), 0] = mins[torch.tensor(src, device=eng.device)]
+        mm[eng.upload(np.asarray(pos, dtype=np.int64)), 0] = mins[eng.upload(np.asarray(src, dtype=np.int64))]
     if unknown:
-        mm[torch.tensor(unknown, device=eng.device)] = eng.minmax_device(base, [idx[n] for n in unknown])
+        mm[eng.upload(np.asarray(unknown, dtype=np.int64))] = eng.minmax_device(base, [idx[n] for n in unknown])
     return mm
 
 
@@ -157,7 +157,9 @@ def detransversalium_many(images, circle, borders, strength):
     h = batch.shape[1]
     with eng.stage('transv_gain'):
         gains_d = eng.transversalium_gains(stats, y1, y2, h, strength)
+    early = eng.download_early(gains_d)
     with eng.stage('row_scale'):
         out = eng.row_scale(batch, gains_d)
-    gains = gains_d.cpu().numpy()                    # options['_transversalium_cache'] is a host array upstream
+    gains = early.result()                           # options['_transversalium_cache'] is a host array upstream;
+    #                                                  copied while the row scaling runs, not behind it
     return [DeviceImage(eng, out[i]) for i in range(len(images))], gains

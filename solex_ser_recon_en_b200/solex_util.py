@@ -206,7 +206,8 @@ def compute_mean_return_fit(vid_rdr, options, hdr, iw, ih, basefich0):
     """Mean frame, slit extent, spectral-line minima and the cubic fit.
     Returns (mean_img uint16 (ih, iw), fit float64 (ih, 4), y1, y2)."""
     eng, stack, mean_dev, max_dev = _mean_max_device(vid_rdr, options, basefich0)
-    mean_img = mean_dev.cpu().numpy()
+    mean_early = eng.download_early(mean_dev)         # copied to the host underneath the line detection
+    mean_img = mean_early.result() if options['save_fit'] or options['flag_display'] else None
     if options['save_fit']:
         fits.PrimaryHDU(mean_img, header=hdr).writeto(output_path(basefich0 + '_mean.fits', options), overwrite='True')
     if options['flag_display']:
@@ -220,6 +221,8 @@ def compute_mean_return_fit(vid_rdr, options, hdr, iw, ih, basefich0):
         det = eng.detect_line(mean_dev, max_dev)
         y1, y2 = det['y1'], det['y2']
         lf = eng.fit_line(det, stack.geom.ih)
+    if mean_img is None:
+        mean_img = mean_early.result()
     logme(basefich0 + '_log.txt', options, 'Vertical limits y1, y2 : ' + str(y1) + ' ' + str(y2))
     p = lf['p3']
     logme(basefich0 + '_log.txt', options, 'Spectral line polynomial fit: ' + str(p))
