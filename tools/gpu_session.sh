@@ -12,3 +12,6 @@ for k in accumulate_u16 recon_tma warp_rows transv_row_stats minmax_u16; do
 done
 timeout 600 python tools/config_bench.py > gpurun_out/config_bench.log 2>&1; tail -16 gpurun_out/config_bench.log
 timeout 300 python tools/kernel_bench.py --only ingest > gpurun_out/ingest_bench.log 2>&1; grep -E "ingest_file|GBps" gpurun_out/ingest_bench.log
+# compute-sanitizer over the kernel / entry-point parity tests (memcheck) and the shared-memory-heavy kernels (racecheck)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_entrypoints.py -m gpu -q > gpurun_out/sanitizer_memcheck.log 2>&1; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/sanitizer_memcheck.log | tail -2
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_kernels.py -m gpu -q -k 'row_stats or recon or warp or gain_kernel or transpose or limb' > gpurun_out/sanitizer_racecheck.log 2>&1; grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/sanitizer_racecheck.log | tail -2
