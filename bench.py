@@ -387,7 +387,7 @@ def run_b200(a):
         recon_bytes = (k1 - k0) * (geom.ih * nb * 2 + len(shifts) * geom.ih * 2)
         t_rec = dev['stages'].get('recon+gather')
         if t_rec:
-            line['roofline_recon'] = {'bound': 'hbm' if world == 1 else 'hbm+nvlink', 'kernel': 'recon_tma_kernel',
+            line['roofline_recon'] = {'bound': 'hbm' if world == 1 else 'hbm+nvlink', 'kernel': 'recon_tma_pair_kernel (pass 2; also tracks each image minimum)',
                                       'achieved': recon_bytes / (t_rec * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                                       'frac': recon_bytes / (t_rec * 1e-3) / 1e9 / peak,
                                       'algorithmic_bytes_per_launch': recon_bytes, 'ms_in_step': t_rec}

@@ -236,10 +236,10 @@ recon_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ S
     }
 }
 
-// Column-pair variant: a thread owns two adjacent columns, so one 32-bit shared-memory load
-// brings both taps of a band row and one 32-bit global store writes both outputs (they are
-// adjacent in the frame-major image).  Half the load / store / address instructions per output,
-// and 128-byte instead of 64-byte store requests per warp (matters for peer writes over NVLink).
+// Column-pair variant: a thread owns two adjacent columns and one 32-bit global store writes both
+// outputs (they are adjacent in the frame-major image): half the store / address instructions per
+// output, and 128-byte instead of 64-byte store requests per warp (matters for peer writes over
+// NVLink).  It also keeps the per-image minimum of what it writes (see s_min).
 __device__ __forceinline__ void st_global_u32(unsigned long long addr, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
@@ -299,22 +299,12 @@ recon_tma_pair_kernel(const __grid_constant__ TmaMaps maps, const __grid_constan
         f0 = fl[i1 + 1]; wl0 = lw[i1 + 1]; wr0 = rw[i1 + 1];
         f1 = fl[i1];     wl1 = lw[i1];     wr1 = rw[i1];
     }
-    const bool same = f0 == f1;
+    // two 16-bit shared-memory loads per band row (one per column).  A single 32-bit load + unpack is
+    // one instruction MORE, and is only valid when both columns sit on the same band row (f0 == f1), which
+    // cost a predicated copy of every load / move in the loop (32 -> 23 instructions per pair).
     auto taps = [&](const T* p0, const T* p1, double& a, double& b) {
-        if (same) {
-            if (sizeof(T) == 2) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(p0);
-                a = u32_to_double(w & 0xffffu);
-                b = u32_to_double(w >> 16);
-            } else {
-                const uint32_t w = *reinterpret_cast<const uint16_t*>(p0);
-                a = u32_to_double((w & 0xffu) << 8);
-                b = u32_to_double(w & 0xff00u);
-            }
-        } else {
-            a = px_to_double<T>(p0[0]);
-            b = px_to_double<T>(p1[0]);
-        }
+        a = px_to_double<T>(p0[0]);
+        b = px_to_double<T>(p1[0]);
     };
     int it = 0;
     for (int64_t k = first; k < n_frames; k += stride, ++it) {
