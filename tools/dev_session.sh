@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "recon" > gpurun_out/t_recon.log 2>&1; tail -3 gpurun_out/t_recon.log
-for cfg in "1 4" "1 2" "0 2"; do set -- $cfg; echo "== recon PAIR=$1 G=$2"; SHG_RECON_PAIR=$1 SHG_RECON_G=$2 timeout 120 python tools/kernel_bench.py --only recon 2>&1 | grep -E '"ms"' | head -1; done
-echo "== bench"; timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_dev.log 2>&1; tail -1 gpurun_out/bench_dev.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stages_ms'])"
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log | cut -c1-600
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_launch.log 2>&1
+for k in recon_tma; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/prof_$k -f python tools/kernel_bench.py --reps 1 --only accumulate,recon,warp,transv,minmax > gpurun_out/ncu_$k.log 2>&1
+  ls -la gpurun_out/prof_$k.ncu-rep 2>/dev/null | awk '{print $5, $9}'
+done
