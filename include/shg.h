@@ -144,6 +144,20 @@ int shg_warp_rows(const uint16_t* d_disk, int64_t disk_stride, const int32_t* d_
                   int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
                   const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows, int out_cols,
                   void* stream);
+/* The same for a scan whose frames are spread over several GPUs: d_disk is a base pointer such that
+ * d_disk + k*ih (+ sel*disk_stride) is frame k of the WHOLE scan, of which this rank holds [own_lo, own_hi]
+ * (logical frame order, i.e. after flip; INT_MIN / INT_MAX = open end).  The call produces exactly the
+ * output pixels whose left tap floor(x) lies in [own_lo, own_hi) -- its own frames plus ONE frame of the
+ * next rank are all it reads, whatever the tilt -- so the ranks' calls tile the image.  d_cval[i]
+ * (optional) replaces the read of image i's pixel [0][0] (the constant for taps outside the image; it
+ * lives on one rank only), and d_out_ptrs[i] (optional, DEVICE array of addresses) replaces
+ * d_out + i*out_stride: the images may live on PEER GPUs (shg_ipc_open), so each rank stores its pixels of
+ * the circularised image straight into the owner's buffer over NVLink. */
+int shg_warp_rows_window(const uint16_t* d_disk, int64_t disk_stride, const int32_t* d_sel, int n_imgs,
+                         int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
+                         const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows,
+                         int out_cols, const uint32_t* d_cval, int own_lo, int own_hi,
+                         const uint64_t* d_out_ptrs, void* stream);
 
 /* ---- a11 helper: 4x4 block sums (reference ellipse_to_circle.py:301) ---- */
 /* downscale_local_mean numerator: out[ri][ci] = sum of the 4x4 block of the

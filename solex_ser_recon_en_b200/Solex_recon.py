@@ -21,7 +21,7 @@ import numpy as np
 
 from . import fits_min as fits
 from . import parallel, postprocess
-from .device_image import DeviceImage
+from .device_image import DeviceImage, PartialImage
 from .ellipse_to_circle import correct_image, ellipse_to_circle, fit_geometry
 from .solex_util import (clearlog, compute_mean_return_fit, correct_transversalium2, image_process, logme,
                          make_header, output_path, read_video_improved, write_complete)
@@ -82,7 +82,7 @@ def solex_read_reader(rdr, options, basefich0):
         if disk_list[i] is None:                              # image owned by another rank
             continue
         if options['flip_x']:
-            disk_list[i] = disk_list[i].flipped() if isinstance(disk_list[i], DeviceImage) \
+            disk_list[i] = disk_list[i].flipped() if isinstance(disk_list[i], (DeviceImage, PartialImage)) \
                 else np.flip(disk_list[i], axis=1)
         if options['save_fit'] and options['shift'][i] in options['shift_requested']:
             basefich = basefich0 + '_shift=' + str(options['shift'][i])
@@ -108,9 +108,43 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
     logme(log, options, f'de-vignette : {options["de-vignette"]}')
     if options['de-vignette']:
         raise Exception('de-vignette is a GUI-only option of the reference and is not part of this path')
+    shifts = options['shift']
+    if options.get('_exchange') == 'post_warp':
+        # frames of every image on every rank (parallel.reconstruct_partial): rank 0 fits the ellipse on the
+        # gathered first image, every rank circularises its own frames, owners receive the result
+        requested, circular, cercle0, borders = _circularise_post_warp(options, disk_list, shifts, basefich0)
+    else:
+        requested, circular, cercle0, borders = _circularise_owned(options, disk_list, shifts, basefich0)
+    # 3. transversalium for all requested shifts (batched), then the host tail per image
+    images = [circular[i] for i in requested]
+    if options['transversalium'] and images and all(isinstance(im, DeviceImage) for im in images) \
+            and not options['save_fit']:
+        if not cercle0 == (-1, -1, -1):
+            circle, bord = cercle0, borders
+        else:
+            circle = (0, 0, 99999)
+            bord = [0, backup_bounds[0] + 20, images[0].shape[1] - 1, backup_bounds[1] - 20]
+        detrans, gains = postprocess.detransversalium_many(images, circle, bord, options['trans_strength'])
+        options['_transversalium_cache'] = gains[-1]
+        options['_transversalium_gains'] = {shifts[i]: gains[j] for j, i in enumerate(requested)}
+    else:
+        detrans = None
+    futures = []
+    for j, i in enumerate(requested):
+        basefich = basefich0 + '_shift=' + str(shifts[i])
+        res = single_image_process(images[j], hdr, options, cercle0, borders, basefich, backup_bounds, _pool=_pool,
+                                   _detrans=None if detrans is None else detrans[j])
+        if _pool is not None:
+            futures.append(res)
+        write_complete(log, options)
+    return futures if _pool is not None else None
+
+
+def _circularise_owned(options, disk_list, shifts, basefich0):
+    """Geometry + circularisation of the requested shifts whose complete disk images this rank holds
+    (all of them on one GPU).  Returns (requested indices, {index: circularised image}, cercle0, borders)."""
     borders = [0, 0, 0, 0]
     cercle0 = (-1, -1, -1)
-    shifts = options['shift']
     # with several ranks each one post-processes the shifts whose images it owns
     requested = [i for i in range(len(disk_list))
                  if shifts[i] in options['shift_requested'] and disk_list[i] is not None]
@@ -151,29 +185,26 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         warped, _, _, _ = postprocess.circularise_many([disk_list[i] for i in todo], phi, ratio,
                                                        prepared if todo == early else None)
         circular.update(zip(todo, warped))
-    # 3. transversalium for all requested shifts (batched), then the host tail per image
-    images = [circular[i] for i in requested]
-    if options['transversalium'] and images and all(isinstance(im, DeviceImage) for im in images) \
-            and not options['save_fit']:
-        if not cercle0 == (-1, -1, -1):
-            circle, bord = cercle0, borders
-        else:
-            circle = (0, 0, 99999)
-            bord = [0, backup_bounds[0] + 20, images[0].shape[1] - 1, backup_bounds[1] - 20]
-        detrans, gains = postprocess.detransversalium_many(images, circle, bord, options['trans_strength'])
-        options['_transversalium_cache'] = gains[-1]
-        options['_transversalium_gains'] = {shifts[i]: gains[j] for j, i in enumerate(requested)}
-    else:
-        detrans = None
-    futures = []
-    for j, i in enumerate(requested):
-        basefich = basefich0 + '_shift=' + str(shifts[i])
-        res = single_image_process(images[j], hdr, options, cercle0, borders, basefich, backup_bounds, _pool=_pool,
-                                   _detrans=None if detrans is None else detrans[j])
-        if _pool is not None:
-            futures.append(res)
-        write_complete(log, options)
-    return futures if _pool is not None else None
+    return requested, circular, cercle0, borders
+
+
+def _circularise_post_warp(options, disk_list, shifts, basefich0):
+    """The same for frame-sharded images (exchange mode 'post_warp'): the list of requested shifts is the
+    same on every rank; the circularised images land on their owners (by position in that list)."""
+    req_all = [i for i in range(len(disk_list)) if shifts[i] in options['shift_requested']]
+    geom = None
+    full0 = disk_list[0].full
+    if full0 is not None:                                     # rank 0: the gathered ellipse-fit image
+        fit = fit_geometry(full0, options, basefich0 + '_shift=' + str(shifts[0]))
+        geom = (tuple(float(v) for v in fit['circle']), float(fit['ratio']), float(fit['phi']),
+                [float(b) for b in fit['borders']])
+    cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_object(geom, src=0)
+    options['slant_fix'] = math.degrees(phi)
+    phi = math.radians(options['slant_fix'])                  # the same degrees round trip as the single-GPU path
+    warped = postprocess.circularise_partial([disk_list[i] for i in req_all], phi, options['ratio_fixe'])
+    requested = [i for q, i in enumerate(req_all) if warped[q] is not None]
+    circular = {i: warped[q] for q, i in enumerate(req_all) if warped[q] is not None}
+    return requested, circular, cercle0, borders
 
 
 def _crop(img, cercle, options):

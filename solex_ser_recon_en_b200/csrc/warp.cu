@@ -12,6 +12,8 @@
 // memory with coalesced loads and writes (ih, Wout) rows with coalesced stores:
 // the warp doubles as the transpose to the reference layout.
 // Bound: HBM, ih*N*2 bytes read + ih*Wout*2 bytes written per image.
+#include <limits.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -30,16 +32,32 @@ __global__ void __launch_bounds__(256)
 warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, const int32_t* __restrict__ sel,
                  int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
                  const uint32_t* __restrict__ minmax /* [n_imgs][2] */,
-                 uint16_t* __restrict__ out_base, int64_t out_stride, int out_rows, int out_cols, int span) {
+                 uint16_t* __restrict__ out_base, int64_t out_stride, int out_rows, int out_cols, int span,
+                 const uint32_t* __restrict__ cval_arr /* [n_imgs] or null */, int own_lo, int own_hi,
+                 const unsigned long long* __restrict__ out_ptrs /* [n_imgs] or null */) {
     extern __shared__ uint16_t tile[];           // [span][kPitch]
     const int img = blockIdx.z;
+    // (frame-sharded scans pass a base pointer such that disk + k*ih is frame k of the WHOLE scan.  This rank
+    // produces exactly the output pixels whose left tap floor(x) lies in its frames [own_lo, own_hi) -- logical
+    // frame order; INT_MIN / INT_MAX = open end -- so only frames [own_lo, own_hi] are touched: its own plus ONE
+    // frame of the next rank, whatever the tilt.  image[0][0] then comes from cval_arr and the output image from
+    // out_ptrs, possibly on a peer GPU: every pixel of it is written by exactly one rank.)
     const uint16_t* disk = disk_base + (int64_t)(sel ? sel[img] : img) * disk_stride;
-    uint16_t* out = out_base + (int64_t)img * out_stride;
-    const double cval = u32_to_double(disk[(flip ? (n_frames - 1) : 0) * (int64_t)ih]);   // image[0][0]
+    uint16_t* out = out_ptrs ? reinterpret_cast<uint16_t*>(out_ptrs[img]) : out_base + (int64_t)img * out_stride;
+    const double cval = cval_arr ? u32_to_double(cval_arr[img])
+                                 : u32_to_double(disk[(flip ? (n_frames - 1) : 0) * (int64_t)ih]);   // image[0][0]
     const int r0 = blockIdx.y * kRows;
-    const int c0 = blockIdx.x * COLS;
     const int r1 = min(r0 + kRows, out_rows);
-    const int c1 = min(c0 + COLS, out_cols);
+    // columns that can hold a pixel of this rank in rows [r0, r1): x = m00*c + m01*r + m02 in [own_lo, own_hi)
+    int cb = 0, ce = out_cols;
+    {
+        const double s0 = m01 * (double)r0, s1 = m01 * (double)(r1 - 1);
+        if (own_lo != INT_MIN) cb = max(0, (int)fmax(floor(((double)own_lo - fmax(s0, s1) - m02) / m00) - 1.0, -1.0e9));
+        if (own_hi != INT_MAX) ce = min(out_cols, (int)fmin(ceil(((double)own_hi - fmin(s0, s1) - m02) / m00) + 1.0, 1.0e9));
+    }
+    const int c0 = cb + blockIdx.x * COLS;
+    if (c0 >= ce) return;
+    const int c1 = min(c0 + COLS, ce);
     // frame range touched by this tile (x is monotone in c and in r)
     double xa = 1e300, xb = -1e300;
     {
@@ -55,6 +73,8 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     // clamp before converting: far outside the image everything is cval anyway
     xa = fmax(xa, -4.0);
     xb = fmin(xb, (double)n_frames + 4.0);
+    if (own_lo != INT_MIN) xa = fmax(xa, (double)own_lo);           // taps of this rank's pixels: frames [own_lo, own_hi]
+    if (own_hi != INT_MAX) xb = fmin(xb, (double)own_hi);
     const int64_t kbase = (int64_t)floor(xa);
     const int64_t kend = min((int64_t)ceil(xb) + 1, kbase + span);   // exclusive
     const int nrow = min(r1, ih) - r0;                                // valid slit rows (may be <= 0)
@@ -111,7 +131,7 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
     __syncthreads();
     constexpr int RGROUPS = 256 / COLS;                                // row groups working side by side
     const int c = c0 + (threadIdx.x % COLS);
-    if (c >= out_cols) return;
+    if (c >= c1) return;
     const double mc = __dmul_rn(m00, (double)c);
     const int ilo = (int)minmax[2 * img], ihi = (int)minmax[2 * img + 1];
     const int kb = (int)kbase, nf = (int)n_frames;
@@ -127,14 +147,16 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
             const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, rd)), m02);
             const double xm = __dadd_rd(x, kMagic);
             const int kf = __double2loint(xm);
-            const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));
-            const uint16_t* p = col + kf * kPitch;
-            const double L = u32_to_double(p[0]);
-            const double R = u32_to_double(p[d != 0.0 ? kPitch : 0]);
-            const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
-            int q = __double2loint(__dadd_rd(v, kMagic));
-            q = min(max(q, ilo), ihi);
-            *o = (uint16_t)q;
+            if (kf >= own_lo && kf < own_hi) {                          // (always, unless the scan is frame-sharded)
+                const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));
+                const uint16_t* p = col + kf * kPitch;
+                const double L = u32_to_double(p[0]);
+                const double R = u32_to_double(p[d != 0.0 ? kPitch : 0]);
+                const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, d), L), __dmul_rn(d, R));
+                int q = __double2loint(__dadd_rd(v, kMagic));
+                q = min(max(q, ilo), ihi);
+                *o = (uint16_t)q;
+            }
             rd += (double)RGROUPS;
             col += RGROUPS;
             o += (int64_t)RGROUPS * out_cols;
@@ -145,6 +167,7 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
         const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
         const double xm = __dadd_rd(x, kMagic);
         const int kf = __double2loint(xm);                              // floor(x) (|x| < 2^31)
+        if (kf < own_lo || kf >= own_hi) continue;                      // another rank's pixel (frame-sharded scans)
         const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));          // x - floor(x), exact subtraction of the integer
         const int kc = kf + (d != 0.0 ? 1 : 0);                         // ceil(x)
         double L = cval, R = cval;
@@ -187,7 +210,18 @@ extern "C" int shg_warp_rows(const uint16_t* d_disk, int64_t disk_stride, const 
                              int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
                              const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows,
                              int out_cols, void* stream) {
+    return shg_warp_rows_window(d_disk, disk_stride, d_sel, n_imgs, n_frames, ih, flip, m00, m01, m02, d_minmax, d_out,
+                                out_stride, out_rows, out_cols, nullptr, INT_MIN, INT_MAX, nullptr, stream);
+}
+
+extern "C" int shg_warp_rows_window(const uint16_t* d_disk, int64_t disk_stride, const int32_t* d_sel, int n_imgs,
+                                    int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
+                                    const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride, int out_rows,
+                                    int out_cols, const uint32_t* d_cval, int own_lo, int own_hi,
+                                    const uint64_t* d_out_ptrs, void* stream) {
     SHG_REQUIRE(n_frames > 0 && ih > 0 && out_rows > 0 && out_cols > 0 && n_imgs > 0, "shg_warp_rows: bad geometry");
+    SHG_REQUIRE(own_lo < own_hi, "shg_warp_rows: empty frame range [%d, %d)", own_lo, own_hi);
+    SHG_REQUIRE(d_out || d_out_ptrs, "shg_warp_rows: no output");
     SHG_REQUIRE(std::isfinite(m00) && std::isfinite(m01) && std::isfinite(m02) && m00 > 0.0,
                 "shg_warp_rows: bad matrix (%g, %g, %g)", m00, m01, m02);
     SHG_REQUIRE(n_imgs <= 65535, "shg_warp_rows: too many images");
@@ -200,14 +234,31 @@ extern "C" int shg_warp_rows(const uint16_t* d_disk, int64_t disk_stride, const 
                 m01);
     const int span = (int)std::ceil(spanf);
     const size_t smem = (size_t)span * kPitch * sizeof(uint16_t);
-    dim3 grid((out_cols + cols - 1) / cols, (out_rows + kRows - 1) / kRows, n_imgs);
+    // widest column window over the row tiles (the kernel derives each tile's window with the same formulas)
+    int max_width = out_cols;
+    if (own_lo != INT_MIN || own_hi != INT_MAX) {
+        max_width = 1;
+        for (int r0 = 0; r0 < out_rows; r0 += kRows) {
+            const int r1 = std::min(r0 + kRows, out_rows);
+            const double s0 = m01 * (double)r0, s1 = m01 * (double)(r1 - 1);
+            int cb = 0, ce = out_cols;
+            if (own_lo != INT_MIN)
+                cb = std::max(0, (int)std::max(std::floor(((double)own_lo - std::max(s0, s1) - m02) / m00) - 1.0, -1.0e9));
+            if (own_hi != INT_MAX)
+                ce = std::min(out_cols, (int)std::min(std::ceil(((double)own_hi - std::min(s0, s1) - m02) / m00) + 1.0, 1.0e9));
+            max_width = std::max(max_width, ce - cb);
+        }
+    }
+    dim3 grid((max_width + cols - 1) / cols, (out_rows + kRows - 1) / kRows, n_imgs);
     SHG_REQUIRE(grid.y <= 65535, "shg_warp_rows: too many rows");
     cudaStream_t st = as_stream(stream);
 #define SHG_WARP_LAUNCH(C)                                                                                          \
     do {                                                                                                            \
         SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         warp_rows_kernel<C><<<grid, 256, smem, st>>>(d_disk, disk_stride, d_sel, n_frames, ih, flip, m00, m01, m02,  \
-                                                     d_minmax, d_out, out_stride, out_rows, out_cols, span);        \
+                                                     d_minmax, d_out, out_stride, out_rows, out_cols, span, d_cval, \
+                                                     own_lo, own_hi,                                                \
+                                                     reinterpret_cast<const unsigned long long*>(d_out_ptrs));      \
     } while (0)
     if (cols == 256) SHG_WARP_LAUNCH(256);
     else if (cols == 128) SHG_WARP_LAUNCH(128);

@@ -111,3 +111,40 @@ class DeviceImage:
 
     def __repr__(self):
         return 'DeviceImage(shape=%s, layout=%s, flip=%s)' % (self.shape, self.layout, self.flip)
+
+
+class PartialImage:
+    """This rank's frame rows of an image whose frames are spread over the GPUs of the box
+    (parallel.reconstruct, exchange mode 'post_warp'): logical shape (ih, N) like every disk image,
+    but only frames [k0, k1) -- plus `halo` frames of each neighbour -- are here.
+    tensor: (halo + (k1 - k0) + halo, ih) frame-major; row r is frame k0 - halo + r of the scan.
+    The pixels of the whole image never exist on one GPU: the circularisation works on the parts and
+    the ranks exchange the (4-5 x smaller) circularised column blocks instead."""
+    dtype = np.dtype(np.uint16)
+    ndim = 2
+
+    def __init__(self, engine, tensor, k0, k1, halo, n_frames, flip=False):
+        self.engine, self.tensor = engine, tensor
+        self.k0, self.k1, self.halo, self.n_frames, self.flip = int(k0), int(k1), int(halo), int(n_frames), bool(flip)
+        self.min_ref = None           # (int32 device tensor, index): minimum pixel of the WHOLE image
+        self.cval_ref = None          # (int32 device tensor, index): pixel [0][0] of the whole image
+        self.full = None              # the complete image, on the rank that also holds it (the ellipse-fit shift)
+        self.fit_future = None
+
+    @property
+    def shape(self):
+        return (int(self.tensor.shape[1]), self.n_frames)
+
+    def flipped(self):
+        out = PartialImage(self.engine, self.tensor, self.k0, self.k1, self.halo, self.n_frames, not self.flip)
+        out.min_ref, out.cval_ref = self.min_ref, self.cval_ref
+        out.full = None if self.full is None else self.full.flipped()
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        raise TypeError('this image is spread over the GPUs (exchange mode post_warp); its pixels exist only after '
+                        'the circularisation.  Set SHG_EXCHANGE=by_shift to have complete disk images on their owners')
+
+    def __repr__(self):
+        return 'PartialImage(shape=%s, frames=[%d, %d), halo=%d, flip=%s)' % (self.shape, self.k0, self.k1, self.halo,
+                                                                            self.flip)

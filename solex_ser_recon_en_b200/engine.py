@@ -466,7 +466,7 @@ class Engine:
         device as an int32 (n, 2) tensor: the warp reads its clip range from it."""
         if imgs.dim() == 2:
             imgs = imgs.unsqueeze(0)
-        assert imgs.is_contiguous()
+        assert imgs[0].is_contiguous()                  # images may be slices of a larger buffer (stride(0) > numel)
         n_imgs = imgs.shape[0] if sel is None else len(sel)
         sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
         mm = self.empty((n_imgs, 2), torch.int32)
@@ -480,9 +480,17 @@ class Engine:
         return int(lo), int(hi)
 
     # -------------------------------------------------- circularisation warp
-    def warp_batch(self, disks, sel, flip: bool, mat3: np.ndarray, out_shape, minmax_dev=None, out=None):
+    def warp_batch(self, disks, sel, flip: bool, mat3: np.ndarray, out_shape, minmax_dev=None, out=None,
+                   n_frames: int | None = None, frame_origin: int = 0, cvals=None, window=None, out_ptrs=None):
         """correct_image's pixel work (ellipse_to_circle.py:112-118) on frame-major
-        disks (S, N, ih): images `sel` (None = all) -> (n, rows, cols) uint16, one launch."""
+        disks (S, N, ih): images `sel` (None = all) -> (n, rows, cols) uint16, one launch.
+
+        Frame-sharded scans (parallel.py, exchange after the warp): `disks` holds PHYSICAL frames
+        [frame_origin, frame_origin + disks.shape[1]) of a scan of `n_frames`; only the output
+        pixels whose left tap lies in the logical frames window = (own_lo, own_hi) are produced,
+        `cvals` (int32 device tensor, one per image) stands in for each image's pixel [0][0], and
+        `out_ptrs` (int64 device tensor, one address per image, possibly on peer GPUs) says where
+        each image goes."""
         if disks.dim() == 2:
             disks = disks.unsqueeze(0)
         assert disks.is_contiguous() or disks.stride(1) == disks.shape[2]
@@ -493,13 +501,24 @@ class Engine:
         n_imgs = disks.shape[0] if sel is None else len(sel)
         sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
         if minmax_dev is None:
+            assert n_frames is None, 'a frame-sharded warp needs the clip range of the whole images'
             minmax_dev = self.minmax_device(disks, sel)
         oh, ow = int(out_shape[0]), int(out_shape[1])
-        if out is None:
-            out = self.empty((n_imgs, oh, ow), torch.uint16)
-        call('shg_warp_rows', disks.data_ptr(), disks.stride(0), _ptr(sel_t), n_imgs, n, ih, 1 if flip else 0,
-             float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), out.data_ptr(),
-             out.stride(0), oh, ow, self.stream)
+        sharded = n_frames is not None
+        if not sharded:
+            if out is None:
+                out = self.empty((n_imgs, oh, ow), torch.uint16)
+            call('shg_warp_rows', disks.data_ptr(), disks.stride(0), _ptr(sel_t), n_imgs, n, ih, 1 if flip else 0,
+                 float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), out.data_ptr(),
+                 out.stride(0), oh, ow, self.stream)
+            self.n_launches += 1
+            return out
+        assert cvals is not None and window is not None and (out is not None or out_ptrs is not None)
+        base = disks.data_ptr() - int(frame_origin) * ih * 2          # frame 0 of the whole scan (never dereferenced there)
+        call('shg_warp_rows_window', base, disks.stride(0), _ptr(sel_t), n_imgs, int(n_frames), ih, 1 if flip else 0,
+             float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), _ptr(out),
+             0 if out is None else out.stride(0), oh, ow, cvals.data_ptr(), int(window[0]), int(window[1]),
+             _ptr(out_ptrs), self.stream)
         self.n_launches += 1
         return out
 

@@ -12,10 +12,14 @@ identity, so the drop-in modules call them unconditionally.
 """
 from __future__ import annotations
 
+import math
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._lib import ShgError
 from .engine import get_engine
 
 
@@ -119,26 +123,44 @@ class RowExchange:
 
 
 _exchange = {}
+# How the ranks exchange what they reconstruct (SHG_EXCHANGE overrides):
+#  'by_shift'  every rank stores its frame rows of image j straight into the rank that owns shift j
+#              (contiguous blocks of the shift list): complete disk images on their owners, 16.5 GB x (G-1)/G
+#              over NVLink at config 5;
+#  'gather0'   the same with every image on rank 0 (north_star's wording);
+#  'post_warp' every rank keeps its frame rows of ALL images, circularises its own frame range (the warp is a
+#              per-row resample along the frame axis) and stores the resulting column block of the 4-5 x smaller
+#              circularised image into the owner: 3.6 GB x (G-1)/G over NVLink.  Only the ellipse-fit image is
+#              gathered (rank 0 fits it).  Used by solex_read + solex_process when nothing needs the pixels of a
+#              complete disk image on one GPU (no -f FITS of the raw disks, no display, no diagnostic plots,
+#              no fixed ratio / tilt); otherwise 'by_shift' is used.
 EXCHANGE_MODE = 'by_shift'
 
 
-def row_exchange(n_shifts, n_frames, ih, mode=None):
-    mode = mode or EXCHANGE_MODE
+def exchange_mode():
+    mode = os.environ.get('SHG_EXCHANGE', EXCHANGE_MODE)
+    if mode not in ('by_shift', 'gather0', 'post_warp'):
+        raise ShgError('SHG_EXCHANGE must be by_shift, gather0 or post_warp, not %r' % mode)
+    return mode
+
+
+def row_exchange(n_shifts, n_frames, ih, mode=None, slot='current'):
+    mode = mode or (EXCHANGE_MODE if EXCHANGE_MODE != 'post_warp' else 'by_shift')
     key = (n_shifts, n_frames, ih, mode)
-    ex = _exchange.get('current')
+    ex = _exchange.get(slot)
     if ex is None or ex.key != key:
         if ex is not None:
             torch.cuda.synchronize()
             dist.barrier()
             ex.close()
         ex = RowExchange(n_shifts, n_frames, ih, mode)
-        _exchange['current'] = ex
+        _exchange[slot] = ex
     return ex
 
 
 def release_exchange():
-    ex = _exchange.pop('current', None)
-    if ex is not None:
+    for slot in list(_exchange):
+        ex = _exchange.pop(slot)
         torch.cuda.synchronize()
         if dist.is_initialized():
             dist.barrier()
@@ -233,6 +255,109 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     for n, j in enumerate(ex.mine):
         out[j] = ex.images[n]
     return out, mins, known
+
+
+# ----------------------------------------------------------------------------
+# exchange mode 'post_warp'
+HALO = 2          # frames of each neighbour kept next to a rank's own: the warp of a pixel whose left tap
+#                   floor(x) is this rank's frame reads frame floor(x) + 1 at most (see shg_warp_rows_window)
+
+
+def halo_frames(n_frames: int, size: int) -> int:
+    return max(1, min(HALO, n_frames // size))
+
+
+def _halo_exchange(local, h: int, n_local: int):
+    """local: (S, h + n_local + h, ih).  Fill the margins with the neighbours' border frames (NCCL P2P)."""
+    rank, size = world()
+    ops, recv = [], {}
+    if rank > 0:
+        send = local[:, h:2 * h].contiguous()
+        recv['l'] = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send.view(torch.uint8), rank - 1),
+                dist.P2POp(dist.irecv, recv['l'].view(torch.uint8), rank - 1)]
+    if rank < size - 1:
+        send2 = local[:, n_local:n_local + h].contiguous()
+        recv['r'] = torch.empty_like(send2)
+        ops += [dist.P2POp(dist.isend, send2.view(torch.uint8), rank + 1),
+                dist.P2POp(dist.irecv, recv['r'].view(torch.uint8), rank + 1)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if 'l' in recv:
+        local[:, :h].copy_(recv['l'])
+    if 'r' in recv:
+        local[:, h + n_local:].copy_(recv['r'])
+
+
+def reconstruct_partial(stack, fit: np.ndarray, shifts, first_done=None):
+    """Exchange mode 'post_warp': reconstruct this rank's frames of EVERY shift into a local buffer with a
+    halo of neighbour frames on each side.  Returns a list of device_image.PartialImage (one per shift, on
+    every rank).  The image of shifts[0] (the ellipse-fit shift) is ALSO gathered on rank 0 -- a single image,
+    by peer stores -- where `first_done(image0, None)` starts the limb search; it is attached as .full there."""
+    from .device_image import DeviceImage, PartialImage
+    eng = get_engine()
+    rank, size = world()
+    g = stack.geom
+    n_s, n_local, n_frames, ih = len(shifts), stack.n, g.n_frames, g.ih
+    h = halo_frames(n_frames, size)
+    local = eng.empty((n_s, n_local + 2 * h, ih), torch.uint16)
+    mins = torch.full((n_s,), 65535, dtype=torch.int32, device=eng.device)
+    split = first_done is not None and n_s > 1
+    if split:
+        ex0 = row_exchange(1, n_frames, ih, mode='gather0', slot='first')
+        torch.cuda.synchronize()
+        dist.barrier()                     # rank 0 is done reading the previous scan's image
+        eng.recon(stack, fit, shifts[:1], out_ptrs=ex0.ptrs[:1], k0_out=stack.k0, impl=1)
+        torch.cuda.synchronize()
+        dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
+    eng.recon(stack, fit, shifts, disk=local, k0_out=h, mins=mins)
+    if not eng.recon_min_done:             # kernel variant without minimum tracking: one pass over the local rows
+        mins = eng.minmax_device(local[:, h:h + n_local])[:, 0].contiguous()
+    if split and rank == 0:
+        first_done(ex0.images[0], None)
+    _halo_exchange(local, h, n_local)
+    # whole-image minimum and the two candidate [0][0] pixels (first / last frame, slit position 0): one all-reduce
+    red = torch.zeros((3, n_s), dtype=torch.int32, device=eng.device)
+    red[0] = -mins
+    as_i16 = local.view(torch.int16)       # (uint16 -> int32 through int16 + mask: plain dtype conversions only)
+    if stack.k0 == 0:
+        red[1] = as_i16[:, h, 0].to(torch.int32) & 0xFFFF
+    if stack.k0 + n_local == n_frames:
+        red[2] = as_i16[:, h + n_local - 1, 0].to(torch.int32) & 0xFFFF
+    dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    red[0] = -red[0]
+    mins_all = red[0]
+    parts = []
+    for j in range(n_s):
+        p = PartialImage(eng, local[j], stack.k0, stack.k0 + n_local, h, n_frames)
+        p.min_ref = (mins_all, j)
+        p.cval_ref = (red, j)
+        parts.append(p)
+    if split and rank == 0:
+        parts[0].full = DeviceImage(eng, ex0.images[0], 'frames')
+    return parts
+
+
+INT_MIN, INT_MAX = -2 ** 31, 2 ** 31 - 1
+
+
+def owned_logical_frames(n_frames: int, rank: int, size: int, flip: bool):
+    """[lo, hi) of the frames rank `rank` holds, in the order the image shows them (a flipped image shows
+    physical frame p at N-1-p), with INT_MIN / INT_MAX for the two ends of the image: the pixels left of
+    frame 0 and right of frame N-1 (constant fill) belong to the first / last range.  The ranges of all
+    ranks tile the integers, so every output pixel of the circularisation has exactly one producer."""
+    k0, k1 = frame_range(n_frames, rank, size)
+    lo, hi = (n_frames - k1, n_frames - k0) if flip else (k0, k1)
+    return (INT_MIN if lo == 0 else lo), (INT_MAX if hi == n_frames else hi)
+
+
+def circ_exchange(n_imgs: int, out_rows: int, out_cols: int):
+    """Peer-writable circularised images (n_imgs of out_rows x out_cols), owners by position in the list."""
+    ex = row_exchange(n_imgs, out_rows, out_cols, mode='by_shift', slot='circ')
+    if getattr(ex, 'ptrs_dev', None) is None:
+        ex.ptrs_dev = get_engine().upload(ex.ptrs.view(np.int64)).view(torch.int64)
+    return ex
 
 
 def broadcast_object(obj, src: int):

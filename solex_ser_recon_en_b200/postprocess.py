@@ -130,6 +130,53 @@ def circularise_many(images, phi, ratio, prepared=None):
     return res, mat, mat3, theta
 
 
+def circularise_partial(parts, phi, ratio):
+    """Exchange mode 'post_warp' (parallel.py): every rank warps ITS frames of every image in `parts`
+    (device_image.PartialImage, all slices of one local buffer) and stores the pixels it produces straight
+    into the rank that owns the image (peer memory).  Returns a list with a row-major DeviceImage for the
+    images this rank owns and None for the others; owners are assigned by position in the list."""
+    import torch.distributed as dist
+    from . import parallel
+    eng = get_engine()
+    rank, size = parallel.world()
+    p0 = parts[0]
+    ih, n_frames = p0.shape
+    flip = p0.flip
+    mat, mat3, out_shape, _, theta = geometry.warp_plan((ih, n_frames), phi, ratio)
+    oh, ow = int(out_shape[0]), int(out_shape[1])
+    ex = parallel.circ_exchange(len(parts), oh, ow)
+    # all parts are slices of the (S, halo + n_local + halo, ih) buffer of parallel.reconstruct_partial
+    n_ext = p0.tensor.shape[0]
+    stride = n_ext * ih
+    base_ptr = min(p.tensor.data_ptr() for p in parts)
+    first = min(parts, key=lambda p: p.tensor.data_ptr()).tensor
+    idx = []
+    for p in parts:
+        off = (p.tensor.data_ptr() - base_ptr) // 2
+        assert off % stride == 0 and p.tensor.is_contiguous() and p.flip == flip and p.tensor.shape == p0.tensor.shape
+        idx.append(off // stride)
+    base = torch.as_strided(first, (max(idx) + 1, n_ext, ih), (stride, ih, 1))
+    mins, red = p0.min_ref[0], p0.cval_ref[0]
+    src = eng.upload(np.asarray([p.min_ref[1] for p in parts], dtype=np.int64))
+    assert all(p.min_ref[0].data_ptr() == mins.data_ptr() and p.cval_ref[0].data_ptr() == red.data_ptr() for p in parts)
+    mm = torch.empty((len(parts), 2), dtype=torch.int32, device=eng.device)
+    mm[:, 0] = mins[src]
+    mm[:, 1] = 65535
+    cvals = red[2 if flip else 1][src].contiguous()                  # image[0][0]: last / first physical frame
+    own_lo, own_hi = parallel.owned_logical_frames(n_frames, rank, size, flip)
+    torch.cuda.synchronize()
+    dist.barrier()                         # the owners are done reading the previous scan's circularised images
+    with eng.stage('warp'):
+        eng.warp_batch(base, idx, flip, mat3, (oh, ow), mm, n_frames=n_frames, frame_origin=p0.k0 - p0.halo,
+                       cvals=cvals, window=(own_lo, own_hi), out_ptrs=ex.ptrs_dev)
+    torch.cuda.synchronize()
+    dist.barrier()                         # every rank's pixels have landed
+    out = [None] * len(parts)
+    for n, q in enumerate(ex.mine):
+        out[q] = DeviceImage(eng, ex.images[n])
+    return out
+
+
 def _stack_rows(eng, images):
     """(S, h, w) tensor of row-major device images (a view when they already are
     consecutive slices of one tensor, else a copy)."""

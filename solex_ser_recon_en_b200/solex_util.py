@@ -272,15 +272,28 @@ def read_video_improved(rdr, fit, options):
         def first_done(image0, ready):
             from .ellipse_to_circle import start_fit
             prefetch['fit'] = start_fit(DeviceImage(eng, image0, 'frames', bool(options.get('flip_x'))), ready)
-    with eng.stage('recon+gather'):
-        disk, mins, known = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
-    # one image per shift; under several ranks only the images this rank owns (None elsewhere)
-    disk_list = [None if d is None else DeviceImage(eng, d, 'frames') for d in disk]
-    for j, im in enumerate(disk_list):
-        if im is not None and known[j]:
-            im.min_ref = (mins, j)                               # the kernel tracked this image's minimum
-    if 'fit' in prefetch and disk_list[0] is not None:
-        disk_list[0].fit_future = prefetch['fit']
+    # several ranks: complete disk images on their owners ('by_shift'), or -- when nothing downstream needs the
+    # pixels of a complete disk on one GPU -- every rank keeps its frame rows and the (4-5 x smaller)
+    # circularised images are exchanged instead ('post_warp', see parallel.py)
+    _, size = parallel.world()
+    post_warp = (size > 1 and parallel.exchange_mode() == 'post_warp' and wants_fit and not options['save_fit']
+                 and not options['flag_display'] and (options['clahe_only'] or options['protus_only']))
+    options['_exchange'] = 'post_warp' if post_warp else None
+    if post_warp:
+        with eng.stage('recon+gather'):
+            disk_list = parallel.reconstruct_partial(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
+        if 'fit' in prefetch and disk_list[0].full is not None:
+            disk_list[0].full.fit_future = prefetch['fit']
+    else:
+        with eng.stage('recon+gather'):
+            disk, mins, known = parallel.reconstruct(stack, np.asarray(fit, dtype=np.float64), shifts, first_done)
+        # one image per shift; under several ranks only the images this rank owns (None elsewhere)
+        disk_list = [None if d is None else DeviceImage(eng, d, 'frames') for d in disk]
+        for j, im in enumerate(disk_list):
+            if im is not None and known[j]:
+                im.min_ref = (mins, j)                           # the kernel tracked this image's minimum
+        if 'fit' in prefetch and disk_list[0] is not None:
+            disk_list[0].fit_future = prefetch['fit']
     if options['flag_display'] and disk_list[1] is not None:
         cv2.namedWindow('disk', cv2.WINDOW_NORMAL)
         cv2.imshow('disk', np.asarray(disk_list[1]))             # disk_list[1] is always shift = 0

@@ -41,15 +41,30 @@ def main():
         disk_list, bounds, hdr = Solex_recon.solex_read(path, dict(opt) if rep else opt)
         if rep == 0:
             shifts = [int(s) for s in opt['shift']]
-            owner = parallel.shift_owner(len(shifts), world, mode)
             assert (int(bounds[0]), int(bounds[1])) == (int(g['y1']), int(g['y2']))
-            for i, d in enumerate(disk_list):
-                if owner[i] == rank:
-                    assert d is not None and np.array_equal(np.asarray(d), g[f'disk{i}']), (rank, shifts[i])
-                else:
-                    assert d is None
+            if mode == 'post_warp':
+                # every rank keeps its frame rows of every image; complete images exist only after the warp
+                from solex_ser_recon_en_b200.device_image import PartialImage
+                assert opt['_exchange'] == 'post_warp' and all(isinstance(d, PartialImage) for d in disk_list)
+                k0, k1 = parallel.frame_range(int(g['disk0'].shape[1]), rank, world)
+                for i, d in enumerate(disk_list):               # its own rows (between the halos) are the reference's
+                    rows = d.tensor[d.halo:d.halo + (k1 - k0)].cpu().numpy().T
+                    want = g[f'disk{i}'][:, ::-1] if case['flip_x'] else g[f'disk{i}']
+                    assert np.array_equal(rows, want[:, k0:k1]), (rank, shifts[i])
+                if rank == 0:
+                    assert np.array_equal(np.asarray(disk_list[0].full), g['disk0'])
+                req = [i for i, s in enumerate(shifts) if s in case['shift']]
+                own = parallel.shift_owner(len(req), world, 'by_shift')
+                mine = [shifts[i] for q, i in enumerate(req) if own[q] == rank]
+            else:
+                owner = parallel.shift_owner(len(shifts), world, mode)
+                for i, d in enumerate(disk_list):
+                    if owner[i] == rank:
+                        assert d is not None and np.array_equal(np.asarray(d), g[f'disk{i}']), (rank, shifts[i])
+                    else:
+                        assert d is None
+                mine = [s for i, s in enumerate(shifts) if owner[i] == rank and s in case['shift']]
             Solex_recon.solex_process(opt, disk_list, bounds, hdr)
-            mine = [s for i, s in enumerate(shifts) if owner[i] == rank and s in case['shift']]
             assert sorted(got) == sorted(mine), (rank, sorted(got), mine)
             for sh, det in got.items():
                 d = np.abs(det.astype(np.int32) - g[f'det_{sh}'].astype(np.int32))

@@ -20,7 +20,7 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize('mode', ['by_shift', 'gather0'])
+@pytest.mark.parametrize('mode', ['by_shift', 'gather0', 'post_warp'])
 @pytest.mark.parametrize('name', ['ser16_rot', 'ser8_rot_flip'])
 def test_two_ranks_match_reference(name, mode, tmp_path):
     if _n_gpus() < 2:

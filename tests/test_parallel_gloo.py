@@ -86,3 +86,30 @@ def test_frame_ranges_tile_the_scan():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[i][1] == r[i + 1][0] for i in range(size - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_post_warp_pixel_ownership_tiles_the_image():
+    """Exchange mode 'post_warp': a circularised pixel is produced by the rank whose (logical) frames contain
+    its left tap floor(x).  For every world size / flip / tilt: exactly one producer per pixel, and the taps
+    it reads are its own physical frames plus at most HALO frames of a neighbour."""
+    sys.path.insert(0, ROOT)
+    from solex_ser_recon_en_b200 import geometry, parallel
+    n_frames, ih = 997, 160
+    for phi, ratio in ((0.0, 0.31), (0.05, 0.25), (-0.2, 1.7)):
+        _, mat3, (oh, ow), _, _ = geometry.warp_plan((ih, n_frames), phi, ratio)
+        r, c = np.meshgrid(np.arange(oh), np.arange(ow), indexing='ij')
+        kf = np.floor(mat3[0, 0] * c + mat3[0, 1] * r + mat3[0, 2]).astype(np.int64)
+        for size in (2, 3, 8):
+            for flip in (False, True):
+                owners = np.zeros(kf.shape, np.int32)
+                for rank in range(size):
+                    lo, hi = parallel.owned_logical_frames(n_frames, rank, size, flip)
+                    mine = (kf >= lo) & (kf < hi)
+                    owners += mine
+                    k0, k1 = parallel.frame_range(n_frames, rank, size)
+                    taps = np.concatenate([kf[mine], kf[mine] + 1])
+                    taps = taps[(taps >= 0) & (taps < n_frames)]            # outside the image: constant fill
+                    phys = n_frames - 1 - taps if flip else taps
+                    h = parallel.halo_frames(n_frames, size)
+                    assert phys.size == 0 or (phys.min() >= k0 - h and phys.max() <= k1 - 1 + h), (size, flip, rank)
+                assert np.all(owners == 1), (phi, size, flip)
