@@ -27,7 +27,7 @@ constexpr int kPitch = kRows + 2;
 // One CTA = 64 slit rows x COLS output columns of one image (blockIdx.z).  The
 // tile width shrinks as the stretch m00 grows so that the staged frame span
 // stays ~45 KB and several CTAs per SM overlap their loads with the fp64 lerp.
-template <int COLS>
+template <int COLS, bool SHARDED>
 __global__ void __launch_bounds__(256)
 warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, const int32_t* __restrict__ sel,
                  int64_t n_frames, int ih, int flip, double m00, double m01, double m02,
@@ -147,7 +147,7 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
             const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, rd)), m02);
             const double xm = __dadd_rd(x, kMagic);
             const int kf = __double2loint(xm);
-            if (kf >= own_lo && kf < own_hi) {                          // (always, unless the scan is frame-sharded)
+            if (!SHARDED || (kf >= own_lo && kf < own_hi)) {            // (always, unless the scan is frame-sharded)
                 const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));
                 const uint16_t* p = col + kf * kPitch;
                 const double L = u32_to_double(p[0]);
@@ -167,7 +167,7 @@ warp_rows_kernel(const uint16_t* __restrict__ disk_base, int64_t disk_stride, co
         const double x = __dadd_rn(__dadd_rn(mc, __dmul_rn(m01, (double)r)), m02);
         const double xm = __dadd_rd(x, kMagic);
         const int kf = __double2loint(xm);                              // floor(x) (|x| < 2^31)
-        if (kf < own_lo || kf >= own_hi) continue;                      // another rank's pixel (frame-sharded scans)
+        if (SHARDED && (kf < own_lo || kf >= own_hi)) continue;         // another rank's pixel (frame-sharded scans)
         const double d = __dsub_rn(x, __dsub_rn(xm, kMagic));          // x - floor(x), exact subtraction of the integer
         const int kc = kf + (d != 0.0 ? 1 : 0);                         // ceil(x)
         double L = cval, R = cval;
@@ -252,17 +252,24 @@ extern "C" int shg_warp_rows_window(const uint16_t* d_disk, int64_t disk_stride,
     dim3 grid((max_width + cols - 1) / cols, (out_rows + kRows - 1) / kRows, n_imgs);
     SHG_REQUIRE(grid.y <= 65535, "shg_warp_rows: too many rows");
     cudaStream_t st = as_stream(stream);
-#define SHG_WARP_LAUNCH(C)                                                                                          \
+#define SHG_WARP_LAUNCH(C, S)                                                                                         \
     do {                                                                                                            \
-        SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        warp_rows_kernel<C><<<grid, 256, smem, st>>>(d_disk, disk_stride, d_sel, n_frames, ih, flip, m00, m01, m02,  \
+        SHG_CHECK(cudaFuncSetAttribute(warp_rows_kernel<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        warp_rows_kernel<C, S><<<grid, 256, smem, st>>>(d_disk, disk_stride, d_sel, n_frames, ih, flip, m00, m01, m02,  \
                                                      d_minmax, d_out, out_stride, out_rows, out_cols, span, d_cval, \
                                                      own_lo, own_hi,                                                \
                                                      reinterpret_cast<const unsigned long long*>(d_out_ptrs));      \
     } while (0)
-    if (cols == 256) SHG_WARP_LAUNCH(256);
-    else if (cols == 128) SHG_WARP_LAUNCH(128);
-    else SHG_WARP_LAUNCH(64);
+    const bool sharded = own_lo != INT_MIN || own_hi != INT_MAX;     // the ownership test compiles out otherwise
+    if (sharded) {
+        if (cols == 256) SHG_WARP_LAUNCH(256, true);
+        else if (cols == 128) SHG_WARP_LAUNCH(128, true);
+        else SHG_WARP_LAUNCH(64, true);
+    } else {
+        if (cols == 256) SHG_WARP_LAUNCH(256, false);
+        else if (cols == 128) SHG_WARP_LAUNCH(128, false);
+        else SHG_WARP_LAUNCH(64, false);
+    }
     SHG_LAUNCH_CHECK();
     return 0;
 }

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x > gpurun_out/tests_multi.log 2>&1; tail -15 gpurun_out/tests_multi.log | cut -c1-400
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x > gpurun_out/tests_multi.log 2>&1; tail -2 gpurun_out/tests_multi.log | cut -c1-300
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_entrypoints.py -m gpu -q -x -k "warp or circular or correct_image or process or entry or cli" > gpurun_out/t_warp.log 2>&1; tail -2 gpurun_out/t_warp.log
-SHG_EXCHANGE=post_warp timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_n2_pw.log 2>&1; tail -1 gpurun_out/bench_n2_pw.log | cut -c1-1200 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['stages_ms'])" || tail -20 gpurun_out/bench_n2_pw.log
+timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_dev.log 2>&1; tail -1 gpurun_out/bench_dev.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stages_ms']['warp'], d['stages_ms'])"
