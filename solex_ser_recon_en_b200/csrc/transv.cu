@@ -671,7 +671,7 @@ log_u16_eval_kernel(double* __restrict__ out) {
     if (v < 65536) out[v] = log_u16((uint32_t)v, seg);
 }
 
-template <int kT, int U>
+template <int kT>
 __global__ void __launch_bounds__(kT, (kT == 64 ? 6 : (kT == 128 ? 6 : (kT == 256 ? 3 : 1))))
 transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
@@ -732,6 +732,7 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     // U elements per thread and trip: the series of all U are evaluated unconditionally (independent
     // dependency chains the scheduler can interleave; a branch per element serialised them), the rare
     // pairs outside its range are redone with two logs; the next trip's pixels are loaded meanwhile.
+    constexpr int U = 4;                             // (eight chains per thread measured slower: 6.9 vs 5.8 ms)
     uint32_t pa[U], pb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1060,22 +1061,16 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     SHG_CHECK(cudaMemcpyToSymbolAsync(g_logseg, g_logseg_host, sizeof(g_logseg_host), 0, cudaMemcpyHostToDevice, st));
 #define SHG_TRANSV_LAUNCH(T)                                                                                        \
     do {                                                                                                            \
-        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                        (int)smem));                                                                 \
-        transv_row_stats_kernel<T, 4><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
+        transv_row_stats_kernel<T><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
                                                           d_out, static_cast<double*>(d_work), pitch, smem_cap,     \
                                                           use_hist);                                                \
     } while (0)
     const int threads = transv_threads(max_len);
     int use_hist = 1;                // SHG_TRANSV_HIST=0: bit-sliced select only; +4 / +8: stop after the rat phase / median (timing)
     if (const char* e = getenv("SHG_TRANSV_HIST")) use_hist = atoi(e);
-    if (threads == 128 && getenv("SHG_TRANSV_U8")) {         // tuning: 8 interleaved chains per thread
-        SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        transv_row_stats_kernel<128, 8><<<grid, 128, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,
-                                                                 d_out, static_cast<double*>(d_work), pitch, smem_cap,
-                                                                 use_hist);
-    } else if (threads == 64) SHG_TRANSV_LAUNCH(64);
+    if (threads == 64) SHG_TRANSV_LAUNCH(64);
     else if (threads == 128) SHG_TRANSV_LAUNCH(128);
     else if (threads == 256) SHG_TRANSV_LAUNCH(256);
     else if (threads == 512) SHG_TRANSV_LAUNCH(512);
