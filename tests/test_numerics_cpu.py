@@ -1,0 +1,57 @@
+"""CPU models of the two in-kernel logarithms of csrc/transv.cu (log_u16, log_ratio_series): the error bounds
+quoted in the kernel comments and in DESIGN.md, checked in extended precision without a GPU.  The GPU tests
+(test_log_u16_matches_numpy, test_row_stats_single_pixel_chords_give_log_ratio) check the kernels themselves."""
+import numpy as np
+
+L = np.longdouble
+
+
+def _fma(a, b, c):
+    """a*b + c rounded once to fp64 (80-bit intermediate: exact enough for these magnitudes)."""
+    return (a.astype(L) * b.astype(L) + c).astype(np.float64)
+
+
+def test_log_u16_model_is_within_one_ulp_of_log_65535():
+    v = np.arange(1, 65536, dtype=np.uint32)
+    e = np.floor(np.log2(v.astype(np.float64))).astype(np.int64)
+    m16 = (v << (15 - e).astype(np.uint32)).astype(np.uint32)
+    assert m16.min() >= 32768 and m16.max() < 65536
+    h = np.arange(128)
+    c = 1.0 / (1.0 + (h + 0.5) / 128.0)                       # the 128-segment table: {c / 2^15, -log(c)}
+    t = (-np.log(c.astype(L))).astype(np.float64)
+    idx = (m16 >> 8) & 127
+    r = _fma(m16.astype(np.float64), (c / 32768.0)[idx], L(-1.0))
+    assert np.abs(r).max() <= 2.0 ** -8                       # the degree-6 log1p remainder is then < 2e-18
+    p = _fma(r, np.full_like(r, -1.0 / 6.0), L(0.2))
+    p = _fma(r, p, L(-0.25))
+    p = _fma(r, p, L(1.0 / 3.0))
+    p = _fma(r, p, L(-0.5))
+    ed = e.astype(np.float64)
+    hi = _fma(ed, np.full_like(r, 6.93147180369123816490e-01), t[idx].astype(L))
+    lo = _fma(ed, np.full_like(r, 1.90821492927058770002e-10), _fma(r * r, p, r.astype(L)).astype(L))
+    got = hi + lo
+    err = np.abs(got.astype(L) - np.log(v.astype(L))).astype(np.float64)
+    assert err.max() <= 2.0e-15                               # ~1 ulp at log(65535) = 11.09
+
+
+def test_log_ratio_series_model_is_a_few_ulp_of_the_result():
+    rng = np.random.default_rng(3)
+    a = rng.integers(1, 65536, 200000).astype(np.int64)
+    b = np.clip(a + rng.integers(-2000, 2001, a.size), 1, 65535)
+    small = (np.abs(a - b) << 6) <= (a + b)                   # the kernel's test for |z| <= 2^-6
+    a, b = a[small], b[small]
+    assert a.size > 50000
+    z = ((a - b).astype(L) / (a + b).astype(L)).astype(np.float64)    # (the kernel's Newton division is <= 1 ulp)
+    z2 = z * z
+    p = _fma(z2, np.full_like(z, 1.0 / 9.0), L(1.0 / 7.0))
+    p = _fma(z2, p, L(0.2))
+    p = _fma(z2, p, L(1.0 / 3.0))
+    got = 2.0 * _fma(z * z2, p, z.astype(L))
+    true = np.log1p((a - b).astype(L) / b.astype(L))
+    err = np.abs(got.astype(L) - true).astype(np.float64)
+    nz = got != 0
+    assert np.all(err[nz] <= 3 * np.spacing(np.abs(got[nz])))
+    assert np.all(got[~nz] == 0) and np.all(true[~nz] == 0)
+    # the reference's own fp64 log(a/b) carries the rounding of the quotient: ~1e-16 absolute
+    ref = np.log(a.astype(np.float64) / b.astype(np.float64))
+    assert np.abs(got - ref).max() <= 2.3e-16
