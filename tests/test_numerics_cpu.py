@@ -55,3 +55,49 @@ def test_log_ratio_series_model_is_a_few_ulp_of_the_result():
     # the reference's own fp64 log(a/b) carries the rounding of the quotient: ~1e-16 absolute
     ref = np.log(a.astype(np.float64) / b.astype(np.float64))
     assert np.abs(got - ref).max() <= 2.3e-16
+
+
+def _counting_select_model(x, t0, t1, qlo, qhi, kind, med=0.0, bins=1024):
+    """NumPy model of hist_select (csrc/transv.cu): one-level counting select with arbitrary bin edges."""
+    keys = x if kind == 0 else np.abs(x - med)
+    iqr = qhi - qlo
+    lo = qlo - 4.0 * iqr if kind == 0 else 0.0
+    scale = (bins - 2) / (9.0 * iqr) if kind == 0 else (bins - 1) / (4.0 * iqr)
+    b = np.floor((keys - lo) * scale).astype(np.int64) + (1 if kind == 0 else 0)
+    b = np.clip(b, 0, bins - 1)
+    counts = np.bincount(b, minlength=bins)
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    b0 = int(np.searchsorted(cum, t0, side='right') - 1)
+    b1 = int(np.searchsorted(cum, t1, side='right') - 1)
+    cand = np.sort(keys[(b >= b0) & (b <= b1)])               # the kernel ranks these exactly in fp64
+    below = cum[b0]
+    return cand[t0 - below], cand[t1 - below], cand.size
+
+
+def test_counting_select_model_is_exact_for_any_bin_edges():
+    """Monotone binning + exact ranking inside the target bins gives the exact order statistics whatever
+    the sample quartiles were -- good edges only keep the candidate list short."""
+    rng = np.random.default_rng(8)
+    for trial in range(60):
+        n = int(rng.integers(257, 4000))
+        x = rng.normal(0.001, 0.01, n)
+        x[rng.integers(0, n, 30)] = rng.uniform(-2.5, 2.5, 30)            # limb pixels
+        if trial % 3 == 0:
+            x = np.round(x, 3)                                             # heavy ties
+        if trial % 2:                                                      # quartiles of a 32-element sample ...
+            s = np.sort(x[((2 * np.arange(32) + 1) * n) >> 6])
+            qlo, qhi = s[8], s[23]
+        else:                                                              # ... or nonsense edges
+            qlo, qhi = sorted(rng.uniform(-1, 1, 2))
+        if not qhi - qlo >= 1e-5:
+            continue
+        t0, t1 = (n - 1) // 2, n // 2
+        srt = np.sort(x)
+        a0, a1, m = _counting_select_model(x, t0, t1, qlo, qhi, 0)
+        assert (a0, a1) == (srt[t0], srt[t1])
+        med = (a0 + a1) / 2.0
+        d = np.sort(np.abs(x - med))
+        b0, b1, _ = _counting_select_model(x, t0, t1, qlo, qhi, 1, med)
+        assert (b0, b1) == (d[t0], d[t1])
+        if trial % 2 and trial % 3:
+            assert m <= 256                                                # representative edges: short candidate list
