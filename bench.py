@@ -424,9 +424,28 @@ def cpu_baseline_subprocess(a):
 
 def main():
     a = parse_args()
-    if a.impl == 'reference':
-        return run_reference_arm(a)
-    return run_b200(a)
+    rank = int(os.environ.get('RANK', '0'))
+    try:
+        if a.impl == 'reference':
+            return run_reference_arm(a)
+        return run_b200(a)
+    except BaseException as e:
+        if isinstance(e, SystemExit) and not e.code:
+            raise
+        # torchrun's own summary pushes a rank's traceback out of the captured tail: say who failed, where, and
+        # leave a per-rank file behind; then take the whole job down so the other ranks do not wait in NCCL
+        import traceback
+        text = 'RANK %d: %s' % (rank, traceback.format_exc())
+        sys.stderr.write(text + '\n')
+        sys.stderr.flush()
+        try:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'bench_rank%d.err' % rank), 'w') as f:
+                f.write(text)
+        except Exception:
+            pass
+        sys.stdout.flush()
+        os._exit(1)
 
 
 if __name__ == '__main__':

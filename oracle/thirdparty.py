@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatements of third-party arithmetic the
 reference calls but which is absent from /root/reference and from this image.
 
-PARITY UNPINNED for everything in this file: the reference's requirements.txt
-names ``scikit-image`` and ``lsq-ellipse`` with no version pin
+PARITY UNPINNED against the packages themselves: the reference's
+requirements.txt names ``scikit-image`` and ``lsq-ellipse`` with no version pin
 (/root/reference/requirements.txt:8-9), neither package is installed here,
 there is no network, and the reference has no tests or golden vectors.  Each
 function restates the package's published algorithm and is anchored on the
@@ -13,9 +13,25 @@ reference call site that uses it:
   ProjectiveTransform/warp  /root/reference/ellipse_to_circle.py:112-114
   LsqEllipse             /root/reference/ellipse_to_circle.py:57-59
 
-Acceptance check in lieu of a pin (tests/test_oracle.py): a synthetic elliptical
-Sun pushed through the *reference's own* two_step + correct_image with these
-stand-ins comes out circular with the row count unchanged.
+CROSS-CHECKED (tests/test_thirdparty_pins.py) against independent
+implementations of the same operations that ARE in this image:
+
+  warp                   scipy.ndimage.map_coordinates(order=1, mode='grid-constant', cval=img[0,0]) + the same
+                         clip / *2**16 / truncation: <= 1 DN on <= 1 pixel in 10^5 (1 pixel of 4.0 M over 35 warps,
+                         a last-ulp truncation), and the committed circ_* fixtures themselves likewise
+  LsqEllipse             a 6x6 generalised-eigenvalue solve of the same constrained conic problem (1e-6: centre,
+                         axes, angle, both phi branches) and cv2.fitEllipseDirect (median 6e-6, 90 % < 5e-5,
+                         max 4e-3 -- OpenCV's own arithmetic is partly single precision), 200 random arcs
+  downscale_local_mean   cv2.resize(INTER_AREA) to 1e-12 on multiples of 4, zero padding worked by hand
+  canny                  its gaussian stage against cv2.sepFilter2D / cv2.GaussianBlur (BORDER_CONSTANT) and its
+                         sobel stage against cv2.Sobel (BORDER_REFLECT) to 1e-12 relative; the whole detector
+                         against cv2.Canny on a fixture's flood image (same boundary within 2 px for >= 95 %).
+                         The interpolated non-maximum suppression and the hysteresis have no bit-level
+                         counterpart here and stay restatements.
+
+Acceptance check (tests/test_oracle.py): a synthetic elliptical Sun pushed
+through the *reference's own* two_step + correct_image with these stand-ins
+comes out circular with the row count unchanged.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
 arm may import this module.  The product never does.
