@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--timeline', action='store_true', help='print the stage timeline of one extra resident pass (stderr)')
     ap.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
+    ap.add_argument('--record-crc', action='store_true',
+                    help='store this run\'s outputs_crc in profiles/outputs_crc.json as the expected value (run at N=1)')
     return ap.parse_args()
 
 
@@ -206,6 +208,68 @@ def run_reference_arm(a):
     return 0
 
 
+# ============================================================ output checksum
+CRC_FILE = os.path.join(ROOT, 'profiles', 'outputs_crc.json')
+
+
+def source_sha():
+    """sha256 of everything that decides the output bits (kernels, host logic, the synthetic scan recipe):
+    a stored checksum is only binding for the build it was recorded with."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, 'solex_ser_recon_en_b200')
+    files = sorted(glob.glob(os.path.join(pkg, 'csrc', '*.cu*')) + glob.glob(os.path.join(pkg, '*.py')) +
+                   [os.path.join(ROOT, 'include', 'shg.h')])
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def outputs_crc(eng, results, shifts, world):
+    """CRC32 over the 64-bit checksums (shg_checksum_u16) of every final image in shift order.  Each image
+    lives on exactly one rank; the per-image values are combined with one all-reduce."""
+    import zlib
+    import torch
+    import torch.distributed as dist
+    vec = torch.zeros(len(shifts), dtype=torch.int64)
+    for j, sh in enumerate(shifts):
+        im = results.get('bench_shift=%d' % sh)
+        if im is not None:
+            v = eng.checksum(im.rows_tensor().contiguous())
+            vec[j] = v - (1 << 64) if v >= (1 << 63) else v
+    if world > 1:
+        dev = vec.to(eng.device)
+        dist.all_reduce(dev, op=dist.ReduceOp.SUM)          # one non-zero contribution per image (mod 2^64)
+        vec = dev.cpu()
+    return '%08x' % (zlib.crc32(vec.numpy().astype('<i8').tobytes()) & 0xffffffff)
+
+
+def crc_key(a, shifts):
+    return '%dx%dx%d_s%d' % (a.frames, a.width, a.height, len(shifts))
+
+
+def check_crc(a, shifts, crc, world):
+    """(expected, match): match is True / False when a value recorded by THIS build exists, else None."""
+    try:
+        book = json.load(open(CRC_FILE))
+    except Exception:
+        book = {}
+    rec = book.get(crc_key(a, shifts))
+    if a.record_crc and world == 1:
+        book[crc_key(a, shifts)] = {'crc': crc, 'source_sha': source_sha(), 'n_gpus': 1}
+        os.makedirs(os.path.dirname(CRC_FILE), exist_ok=True)
+        with open(CRC_FILE, 'w') as f:
+            json.dump(book, f, indent=1, sort_keys=True)
+        return crc, True
+    if rec is None:
+        return None, None
+    if rec.get('source_sha') != source_sha():
+        return rec['crc'], (True if rec['crc'] == crc else None)     # other build: informative only
+    return rec['crc'], rec['crc'] == crc
+
+
 # ================================================================== GPU arm
 def run_b200(a):
     import torch
@@ -284,17 +348,28 @@ def run_b200(a):
 
     # ---- value: stack resident in HBM
     dev = timed_loop(lambda: device_scan(stack), a.steps, a.warmup, False, 'device')
+    dev['crc'] = outputs_crc(eng, results, shifts, world)          # images of the LAST timed step (outside the timing)
 
-    if a.timeline and rank == 0:
+    if a.timeline:                                   # every rank runs the pass (it has collectives); rank 0 prints
         eng.profile_stages = True
         eng.stage_report()
+        barrier()
         t0 = time.perf_counter()
         one_pass(device_scan(stack), False)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
-        for name, s0, s1 in sorted(eng.stage_timeline(), key=lambda t: t[1]):
-            print('timeline %-28s %8.3f -> %8.3f  (%.3f ms)' % (name, s0, s1, s1 - s0), file=sys.stderr)
-        print('timeline wall %.3f ms' % wall, file=sys.stderr)
+        tl = sorted(eng.stage_timeline(), key=lambda t: t[1])
+        lines = ['timeline r%d %-28s gpu %8.3f -> %8.3f (%.3f ms)   host %8.3f -> %8.3f' %
+                 (rank, name, s0, s1, s1 - s0, h0, h1) for name, s0, s1, h0, h1 in tl]
+        lines.append('timeline r%d wall %.3f ms' % (rank, wall))
+        if rank == 0:
+            print('\n'.join(lines), file=sys.stderr)
+        try:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'timeline_n%d_rank%d.txt' % (world, rank)), 'w') as f:
+                f.write('\n'.join(lines) + '\n')
+        except Exception:
+            pass
         eng.profile_stages = False
 
     # ---- e2e: payload in pinned host memory -> H2D -> ... -> D2H
@@ -326,6 +401,7 @@ def run_b200(a):
         pcie_peak = probe / (best * 1e-3) / 1e9
         e_steps = a.e2e_steps or a.steps
         e2e = timed_loop(host_reader, e_steps, min(a.warmup, 3), True, 'e2e')
+        e2e['crc'] = outputs_crc(eng, results, shifts, world)
         e2e['h2d'] = a.frames * geom.frame_bytes
         e2e['pcie_peak'] = pcie_peak
         if world > 1:
@@ -374,7 +450,7 @@ def run_b200(a):
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dev['ms_per_step'], 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic',
             'config': dict(cfg, parallelism='frames sharded over %d rank(s); images owned by shift block' % world),
-            'clocks': clocks, 'gpu_launches': dev['launches'],
+            'clocks': clocks, 'gpu_launches': dev['launches'], 'outputs_crc': dev['crc'],
             'stages_ms': {k: round(v, 3) for k, v in sorted(dev['stages'].items())},
             'roofline': {'bound': 'hbm', 'kernel': 'accumulate_u16_kernel (pass 1: integer sum + max of the stack)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -399,9 +475,22 @@ def run_b200(a):
                            'pcie_h2d_peak_GBps_per_gpu': e2e['pcie_peak'],
                            'pcie_frac': e2e['h2d'] / (e2e['ms_per_step'] * 1e-3) / 1e9 / (e2e['pcie_peak'] * world),
                            'stages_ms': {k: round(v, 3) for k, v in sorted(e2e['stages'].items())}}
+        expected, match = check_crc(a, shifts, dev['crc'], world)
+        line['outputs_crc_expected'] = expected
+        line['outputs_crc_match'] = match
+        line['outputs_crc_note'] = ('CRC32 over the 64-bit position-sensitive checksums of the %d final images in shift '
+                                    'order (last timed step); expected = the value recorded at N=1 by '
+                                    'bench.py --record-crc (profiles/outputs_crc.json), binding when recorded with '
+                                    'this build (source sha %s)' % (len(shifts), source_sha()))
+        if e2e is not None:
+            line['e2e']['outputs_crc'] = e2e['crc']
         if world == 1 and not a.no_cpu:
             line['cpu_baseline'] = cpu_baseline_subprocess(a)
         print(json.dumps(line))
+        sys.stdout.flush()
+        if match is False or (e2e is not None and e2e['crc'] != dev['crc']):
+            raise AssertionError('outputs_crc mismatch: resident %s, e2e %s, expected %s (N=1, this build)' %
+                                 (dev['crc'], e2e['crc'] if e2e else None, expected))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -130,6 +130,12 @@ int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t cols, uint16_t
 int shg_minmax_u16(const uint16_t* d_in, int64_t n, int64_t img_stride, const int32_t* d_sel, int n_imgs,
                    uint32_t* d_out, void* stream);
 
+/* Position-sensitive 64-bit checksum of n uint16 values: *d_out = sum_i (v[i] + 1) * (mix(i) | 1) mod 2^64 with
+ * mix(i) = t ^ (t >> 29), t = (i + 1) * 0x9E3779B97F4A7C15.  Integer, order-independent.  bench.py folds the
+ * checksums of the final images (reference Solex_recon.py:136-152 output, one per requested shift) into the
+ * `outputs_crc` it prints, so that runs on 1, 2, 4 and 8 GPUs can be compared bit for bit. */
+int shg_checksum_u16(const uint16_t* d_in, int64_t n, uint64_t* d_out, void* stream);
+
 /* ---- a10: circularisation warp (reference ellipse_to_circle.py:94-118) -- */
 /* Per-row 1-D linear resample of frame-major disks (n_frames x ih each), batched
  * over n_imgs images that share the geometry (every shift of one scan):
@@ -200,6 +206,34 @@ int shg_sobel_mag(const double* d_smoothed, int rows, int cols, double* d_gi, do
 int shg_nms_candidates(const double* d_gi, const double* d_gj, const double* d_mag, int rows, int cols,
                        double low, uint32_t* d_count, uint32_t cap, uint32_t* d_list_idx,
                        double* d_list_mag, void* stream);
+
+/* The whole threshold search of get_flood_image + the median behind canny's thresholds (reference
+ * ellipse_to_circle.py:148-175, 243-244) as ONE queue of kernels with every data-dependent scalar kept on the
+ * device, and one blocking read-back at the end (the step-by-step entry points above cost ~15 round trips):
+ *   box  = bw x bw box sums of S, box5 = 5 x 5 box sums (d_box, d_box5, d_tmp: rows*cols uint32 each);
+ *   order statistics h_ranks4 = {two ranks in box (np.percentile's bracket), two ranks in box5 (np.median's)};
+ *   ceiling = np.percentile(blurred, q) from its bracket with interpolation weight `gamma`;
+ *   edges = np.linspace(min, max of blurred < ceiling, n_bins + 1); counts = np.histogram on those edges.
+ * d_state: shg_limb_state_bytes() bytes of device scratch.  h_out (>= 8 + 33 + 32 doubles), all exact:
+ *   [0] sum of S, [1..4] the four order statistics (box sums), [5] ceiling, [6] [7] min / max box sum below
+ *   the ceiling, [8 .. 8+n_bins] edges, [41 .. 41+n_bins) counts.  Synchronises the stream. */
+int64_t shg_limb_state_bytes(void);
+int shg_limb_front(const uint32_t* d_sums, int rows, int cols, int bw, const int64_t* h_ranks4, double gamma,
+                   int n_bins, uint32_t* d_box, uint32_t* d_box5, uint32_t* d_tmp, void* d_state, double* h_out,
+                   void* stream);
+/* shg_flood_smooth + shg_sobel_mag + shg_nms_candidates queued back to back, then the candidate count and
+ * the first `first_chunk` list entries copied to the host in one round trip (the rest, if any, in a second).
+ * d_buf6: six rows*cols double images.  *h_count may exceed cap (list truncated: retry with a larger cap).
+ * h_list_*: host buffers of `cap` entries (pinned for speed).  Synchronises the stream. */
+int shg_limb_canny(const uint32_t* d_box, int rows, int cols, double scale, double level, const double* h_weights,
+                   int radius, double eps, double low, double* d_buf6, uint32_t* d_count, uint32_t cap,
+                   uint32_t* d_list_idx, double* d_list_mag, uint32_t first_chunk, uint32_t* h_count,
+                   uint32_t* h_list_idx, double* h_list_mag, void* stream);
+
+/* HOST helper (no GPU): indices of the strict convex-hull vertices of n integer points (x0,y0,x1,y1,...),
+ * in hull order; collinear points on a hull edge are not vertices (the set scipy.spatial.ConvexHull(...).vertices
+ * reports; reference ellipse_to_circle.py:263-269 only tests which regions own a hull vertex). */
+int shg_hull_vertices(const int64_t* h_xy, int64_t n, int64_t* h_vertex_index, int64_t* h_n_vertices);
 
 /* HOST helper (no GPU): 8-connected components of a sparse pixel list (flat = row*cols + col,
  * strictly ascending), labelled 1.. in raster order of each component's first pixel, i.e. what

@@ -23,6 +23,7 @@ from . import fits_min as fits
 from . import parallel, postprocess
 from .device_image import DeviceImage, PartialImage
 from .ellipse_to_circle import correct_image, ellipse_to_circle, fit_geometry
+from .engine import get_engine
 from .solex_util import (clearlog, compute_mean_return_fit, correct_transversalium2, image_process, logme,
                          make_header, output_path, read_video_improved, write_complete)
 from .video_reader import video_reader
@@ -157,18 +158,22 @@ def _circularise_owned(options, disk_list, shifts, basefich0):
     prepared = postprocess.start_minmax([disk_list[i] for i in early])
     # 1. geometry: disk_list[0] is the ellipse-fit shift; the fit is made once (by its owner) and reused
     if options['ratio_fixe'] is None and options['slant_fix'] is None:
-        geom = None
+        geom, failure = None, None
         if disk_list[0] is not None:
             basefich = basefich0 + '_shift=' + str(shifts[0])
             plots = not options['clahe_only'] and not options['protus_only']
-            if plots and 0 in requested:
-                # diagnostic figure wanted: the one-image path draws it
-                circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
-            else:
-                fit = fit_geometry(disk_list[0], options, basefich)
-                cercle0, ratio_fit, phi, borders = fit['circle'], fit['ratio'], fit['phi'], fit['borders']
-            geom = (tuple(float(v) for v in cercle0), float(ratio_fit), float(phi), [float(b) for b in borders])
-        cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_object(geom, src=0)
+            try:
+                if plots and 0 in requested:
+                    # diagnostic figure wanted: the one-image path draws it
+                    circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+                else:
+                    fit = fit_geometry(disk_list[0], options, basefich)
+                    cercle0, ratio_fit, phi, borders = fit['circle'], fit['ratio'], fit['phi'], fit['borders']
+                geom = (tuple(float(v) for v in cercle0), float(ratio_fit), float(phi), [float(b) for b in borders])
+            except Exception as e:                            # the other ranks must not wait for a result
+                failure = e
+        with get_engine().stage('geometry_bcast'):
+            cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_geometry(geom, 0, failure)
         options['slant_fix'] = math.degrees(phi)
         todo = [i for i in requested if i not in circular]
     else:
@@ -192,13 +197,17 @@ def _circularise_post_warp(options, disk_list, shifts, basefich0):
     """The same for frame-sharded images (exchange mode 'post_warp'): the list of requested shifts is the
     same on every rank; the circularised images land on their owners (by position in that list)."""
     req_all = [i for i in range(len(disk_list)) if shifts[i] in options['shift_requested']]
-    geom = None
+    geom, failure = None, None
     full0 = disk_list[0].full
     if full0 is not None:                                     # rank 0: the gathered ellipse-fit image
-        fit = fit_geometry(full0, options, basefich0 + '_shift=' + str(shifts[0]))
-        geom = (tuple(float(v) for v in fit['circle']), float(fit['ratio']), float(fit['phi']),
-                [float(b) for b in fit['borders']])
-    cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_object(geom, src=0)
+        try:
+            fit = fit_geometry(full0, options, basefich0 + '_shift=' + str(shifts[0]))
+            geom = (tuple(float(v) for v in fit['circle']), float(fit['ratio']), float(fit['phi']),
+                    [float(b) for b in fit['borders']])
+        except Exception as e:
+            failure = e
+    with get_engine().stage('geometry_bcast'):
+        cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_geometry(geom, 0, failure)
     options['slant_fix'] = math.degrees(phi)
     phi = math.radians(options['slant_fix'])                  # the same degrees round trip as the single-GPU path
     warped = postprocess.circularise_partial([disk_list[i] for i in req_all], phi, options['ratio_fixe'])

@@ -45,6 +45,7 @@ _PROTOS = {
     'shg_ipc_close': (i32, [vp]),
     'shg_transpose_u16': (i32, [vp, i64, i64, vp, i32, vp]),
     'shg_minmax_u16': (i32, [vp, i64, i64, vp, i32, vp, vp]),
+    'shg_checksum_u16': (i32, [vp, i64, vp, vp]),
     'shg_warp_rows': (i32, [vp, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp]),
     'shg_warp_rows_window': (i32, [vp, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp, i32, i32,
                                    vp, vp]),
@@ -57,6 +58,11 @@ _PROTOS = {
     'shg_flood_smooth': (i32, [vp, i32, i32, dbl, dbl, C.POINTER(dbl), i32, dbl, vp, vp, vp]),
     'shg_sobel_mag': (i32, [vp, i32, i32, vp, vp, vp, vp]),
     'shg_nms_candidates': (i32, [vp, vp, vp, i32, i32, dbl, vp, C.c_uint32, vp, vp, vp]),
+    'shg_limb_state_bytes': (i64, []),
+    'shg_limb_front': (i32, [vp, i32, i32, i32, C.POINTER(i64), dbl, i32, vp, vp, vp, vp, C.POINTER(dbl), vp]),
+    'shg_limb_canny': (i32, [vp, i32, i32, dbl, dbl, C.POINTER(dbl), i32, dbl, dbl, vp, vp, C.c_uint32, vp, vp,
+                             C.c_uint32, vp, vp, vp, vp]),
+    'shg_hull_vertices': (i32, [vp, i64, vp, C.POINTER(i64)]),
     'shg_label_points': (i32, [vp, i64, i64, vp, C.POINTER(C.c_int32)]),
     'shg_log_table': (i32, [vp, vp]),
     'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),

@@ -88,7 +88,32 @@ __global__ void minmax_init_kernel(unsigned int* out, int n_imgs) {
     if (i < n_imgs) { out[2 * i] = 0xffffu; out[2 * i + 1] = 0; }
 }
 
+// position-sensitive checksum of one image: sum over pixels of (v + 1) * odd(mix(index)) mod 2^64.
+// Integer and order-independent, so every launch geometry (and every sharding of the work that produced
+// the image) gives the same value for the same pixels.
+__global__ void __launch_bounds__(256)
+checksum_u16_kernel(const uint16_t* __restrict__ in, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        unsigned long long m = (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+        m ^= m >> 29;
+        acc += ((unsigned long long)in[i] + 1ull) * (m | 1ull);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 }  // namespace
+
+extern "C" int shg_checksum_u16(const uint16_t* d_in, int64_t n, uint64_t* d_out, void* stream) {
+    SHG_REQUIRE(d_out && (d_in || n == 0) && n >= 0, "shg_checksum_u16: bad arguments");
+    SHG_CHECK(cudaMemsetAsync(d_out, 0, 8, as_stream(stream)));
+    if (n == 0) return 0;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256 * 8), SHG_SM_COUNT_B200 * 8));
+    checksum_u16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_in, n, reinterpret_cast<unsigned long long*>(d_out));
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int shg_transpose_u16(const uint16_t* d_in, int64_t rows, int64_t cols, uint16_t* d_out, int flip,
                                  void* stream) {

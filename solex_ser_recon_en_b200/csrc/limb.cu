@@ -211,6 +211,138 @@ nms_kernel(const double* __restrict__ gi, const double* __restrict__ gj, const d
     }
 }
 
+// ---------------------------------------------------------------------------
+// Chained front end (shg_limb_front): every data-dependent scalar of the flood
+// threshold search -- the four order statistics, the percentile, the histogram
+// range, its 21 edges -- stays in a small device-resident block, so the ~20
+// kernels queue back to back and the host reads ONE block back at the end
+// (the step-by-step entry points above cost ~15 blocking round trips).
+struct LimbState {
+    unsigned long long total;          // sum of the block sums
+    unsigned long long counts[32];     // histogram of the blurred image below the ceiling
+    double ceiling;
+    double edges[33];
+    long long rank[4];                 // remaining rank of each order statistic inside its prefix group
+    uint32_t prefix[4];                // value bits decided so far (queries 0,1: box; 2,3: box5)
+    uint32_t range[2];                 // min / max box sum below the ceiling
+    uint32_t hist[4][4][256];          // [pass][query][byte]
+};
+
+// byte histograms of one radix pass for both arrays (blockIdx.y = array); the two queries of an
+// array share a histogram while their prefixes agree
+__global__ void __launch_bounds__(256)
+select_pass_kernel(const uint32_t* __restrict__ v0, const uint32_t* __restrict__ v1, int64_t n, int pass,
+                   LimbState* __restrict__ st) {
+    __shared__ unsigned int h[2][256];
+    const int arr = blockIdx.y;
+    const uint32_t* __restrict__ v = arr ? v1 : v0;
+    h[0][threadIdx.x] = 0;
+    h[1][threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 24 - 8 * pass, hi_shift = shift + 8;
+    const uint32_t p0 = st->prefix[2 * arr], p1 = st->prefix[2 * arr + 1];
+    const bool split = p0 != p1;
+    // the blurred background is nearly constant: most keys of a warp fall into ONE bin, so the lanes that share
+    // a bin elect a leader that adds their count once (a plain shared atomic would serialise 32 ways)
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * 256) {
+        const bool live = i < n;
+        const uint32_t k = live ? v[i] : 0u;
+        const uint32_t top = hi_shift >= 32 ? 0u : (k >> hi_shift);
+        int slot = -1;                                            // 0..255: histogram 0, 256..511: histogram 1
+        if (live && top == p0) slot = (int)((k >> shift) & 255u);
+        else if (live && split && top == p1) slot = 256 + (int)((k >> shift) & 255u);
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[0][0] + slot, (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (h[0][threadIdx.x]) atomicAdd(&st->hist[pass][2 * arr][threadIdx.x], h[0][threadIdx.x]);
+    if (split && h[1][threadIdx.x]) atomicAdd(&st->hist[pass][2 * arr + 1][threadIdx.x], h[1][threadIdx.x]);
+}
+
+__global__ void select_step_kernel(int pass, LimbState* __restrict__ st) {
+    const int q = threadIdx.x;
+    if (q >= 4) return;
+    const uint32_t mine = st->prefix[q], mate = st->prefix[q & ~1];
+    const unsigned int* h = st->hist[pass][(q & 1) && mine == mate ? q - 1 : q];
+    long long r = st->rank[q];
+    int b = 0;
+    for (; b < 255; ++b) {
+        if (r < (long long)h[b]) break;
+        r -= h[b];
+    }
+    __syncwarp(0xf);                                   // every query has read the shared prefixes
+    st->rank[q] = r;
+    st->prefix[q] = (mine << 8) | (uint32_t)b;
+}
+
+// np.percentile(blurred, 99) from its two bracketing order statistics (method 'linear', numpy's _lerp)
+__global__ void limb_ceiling_kernel(double scale, double gamma, double one_minus_gamma, LimbState* __restrict__ st) {
+    const double a = blurred_of(st->prefix[0], scale), b = blurred_of(st->prefix[1], scale);
+    const double diff = __dsub_rn(b, a);
+    double out = __dadd_rn(a, __dmul_rn(diff, gamma));
+    if (gamma >= 0.5) out = __dsub_rn(b, __dmul_rn(diff, one_minus_gamma));
+    st->ceiling = out;
+    st->range[0] = 0xffffffffu;
+    st->range[1] = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+blur_range_dev_kernel(const uint32_t* __restrict__ box, int64_t n, double scale, LimbState* __restrict__ st) {
+    const double ceiling = st->ceiling;
+    unsigned int lo = 0xffffffffu, hi = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const uint32_t b = box[i];
+        if (blurred_of(b, scale) < ceiling) { lo = min(lo, b); hi = max(hi, b); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&st->range[0], lo); atomicMax(&st->range[1], hi); }
+}
+
+// np.histogram's bin edges: np.linspace(first, last, n_bins + 1) = arange * step + first, end point forced
+__global__ void limb_edges_kernel(double scale, int n_bins, LimbState* __restrict__ st) {
+    const int i = threadIdx.x;
+    if (i > n_bins) return;
+    double first, last;
+    if (st->range[0] > st->range[1]) { first = 0.0; last = 1.0; }             // nothing below the ceiling
+    else { first = blurred_of(st->range[0], scale); last = blurred_of(st->range[1], scale); }
+    if (first == last) { first = __dsub_rn(first, 0.5); last = __dadd_rn(last, 0.5); }
+    const double delta = __dsub_rn(last, first);
+    const double step = __ddiv_rn(delta, (double)n_bins);
+    double y;
+    if (step == 0.0) y = __dmul_rn(__ddiv_rn((double)i, (double)n_bins), delta);
+    else y = __dmul_rn((double)i, step);
+    y = __dadd_rn(y, first);
+    if (i == n_bins) y = last;
+    st->edges[i] = y;
+}
+
+__global__ void __launch_bounds__(256)
+blur_hist_dev_kernel(const uint32_t* __restrict__ box, int64_t n, double scale, int n_bins, LimbState* __restrict__ st) {
+    __shared__ unsigned int h[32];
+    __shared__ double e[33];
+    if (threadIdx.x < 32) h[threadIdx.x] = 0;
+    if (threadIdx.x <= n_bins) e[threadIdx.x] = st->edges[threadIdx.x];
+    __syncthreads();
+    const double ceiling = st->ceiling, first = e[0], last = e[n_bins];
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * 256) {
+        int b = -1;
+        if (i < n) {
+            const double x = blurred_of(box[i], scale);
+            if (x < ceiling && !(x < first) && !(x > last)) {
+                b = 0;
+                for (int j = 1; j < n_bins; ++j) b += x >= e[j] ? 1 : 0;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, b);      // lanes of one bin add once (see the select pass)
+        if (b >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[b], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(&st->counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
 unsigned grid_for(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256), 148 * 16)); }
 
 }  // namespace
@@ -334,5 +466,141 @@ extern "C" int shg_nms_candidates(const double* d_gi, const double* d_gj, const 
     nms_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(d_gi, d_gj, d_mag, rows, cols, low, d_count,
                                                                           cap, d_list_idx, d_list_mag);
     SHG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t shg_limb_state_bytes(void) { return (int64_t)sizeof(LimbState); }
+
+extern "C" int shg_limb_front(const uint32_t* d_sums, int rows, int cols, int bw, const int64_t* h_ranks4,
+                              double gamma, int n_bins, uint32_t* d_box, uint32_t* d_box5, uint32_t* d_tmp,
+                              void* d_state, double* h_out, void* stream) {
+    SHG_REQUIRE(d_sums && d_box && d_box5 && d_tmp && d_state && h_out && h_ranks4, "shg_limb_front: null argument");
+    SHG_REQUIRE(n_bins >= 1 && n_bins <= 32, "shg_limb_front: 1..32 bins");
+    SHG_REQUIRE(bw >= 1 && bw <= rows && bw <= cols && rows >= 5 && cols >= 5,
+                "shg_limb_front: image %dx%d too small for the %d px blur", rows, cols, bw);
+    SHG_REQUIRE((int64_t)bw * bw * (16LL * 65535) < 0xffffffffLL, "shg_limb_front: window too large for 32-bit sums");
+    const int64_t n = (int64_t)rows * cols;
+    for (int q = 0; q < 4; ++q)
+        SHG_REQUIRE(h_ranks4[q] >= 0 && h_ranks4[q] < n, "shg_limb_front: rank %lld out of range", (long long)h_ranks4[q]);
+    cudaStream_t st = as_stream(stream);
+    LimbState* S = static_cast<LimbState*>(d_state);
+    LimbState init;
+    memset(&init, 0, offsetof(LimbState, hist));
+    for (int q = 0; q < 4; ++q) init.rank[q] = h_ranks4[q];
+    SHG_CHECK(cudaMemsetAsync(S, 0, sizeof(LimbState), st));
+    // (the head of the block is small enough for the driver to embed the host copy in the command stream)
+    SHG_CHECK(cudaMemcpyAsync(S, &init, offsetof(LimbState, hist), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)ceil_div64(n, 256);
+    sum_u32_kernel<<<grid_for(n), 256, 0, st>>>(d_sums, n, &S->total);
+    hsum_u32_kernel<<<blocks, 256, 0, st>>>(d_sums, rows, cols, bw, d_tmp);
+    vsum_u32_kernel<<<blocks, 256, 0, st>>>(d_tmp, rows, cols, bw, d_box);
+    hsum_u32_kernel<<<blocks, 256, 0, st>>>(d_sums, rows, cols, 5, d_tmp);
+    vsum_u32_kernel<<<blocks, 256, 0, st>>>(d_tmp, rows, cols, 5, d_box5);
+    const dim3 sel_grid(std::max(1u, grid_for(n) / 2), 2);
+    for (int pass = 0; pass < 4; ++pass) {
+        select_pass_kernel<<<sel_grid, 256, 0, st>>>(d_box, d_box5, n, pass, S);
+        select_step_kernel<<<1, 32, 0, st>>>(pass, S);
+    }
+    const double scale = 1.0 / ((double)bw * bw);
+    limb_ceiling_kernel<<<1, 1, 0, st>>>(scale, gamma, 1.0 - gamma, S);
+    blur_range_dev_kernel<<<grid_for(n), 256, 0, st>>>(d_box, n, scale, S);
+    limb_edges_kernel<<<1, 64, 0, st>>>(scale, n_bins, S);
+    blur_hist_dev_kernel<<<grid_for(n), 256, 0, st>>>(d_box, n, scale, n_bins, S);
+    SHG_LAUNCH_CHECK();
+    LimbState head;
+    SHG_CHECK(cudaMemcpyAsync(&head, S, offsetof(LimbState, hist), cudaMemcpyDeviceToHost, st));
+    SHG_CHECK(cudaStreamSynchronize(st));
+    h_out[0] = (double)head.total;
+    for (int q = 0; q < 4; ++q) h_out[1 + q] = (double)head.prefix[q];
+    h_out[5] = head.ceiling;
+    h_out[6] = (double)head.range[0];
+    h_out[7] = (double)head.range[1];
+    for (int i = 0; i <= n_bins; ++i) h_out[8 + i] = head.edges[i];
+    for (int i = 0; i < n_bins; ++i) h_out[8 + 33 + i] = (double)head.counts[i];
+    return 0;
+}
+
+extern "C" int shg_limb_canny(const uint32_t* d_box, int rows, int cols, double scale, double level,
+                              const double* h_weights, int radius, double eps, double low, double* d_buf6,
+                              uint32_t* d_count, uint32_t cap, uint32_t* d_list_idx, double* d_list_mag,
+                              uint32_t first_chunk, uint32_t* h_count, uint32_t* h_list_idx, double* h_list_mag,
+                              void* stream) {
+    SHG_REQUIRE(d_buf6 && d_count && d_list_idx && d_list_mag && h_count && h_list_idx && h_list_mag,
+                "shg_limb_canny: null argument");
+    const int64_t n = (int64_t)rows * cols;
+    cudaStream_t st = as_stream(stream);
+    double* smoothed = d_buf6;
+    int rc = shg_flood_smooth(d_box, rows, cols, scale, level, h_weights, radius, eps, smoothed, d_buf6 + n, stream);
+    if (rc) return rc;
+    rc = shg_sobel_mag(smoothed, rows, cols, d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, stream);
+    if (rc) return rc;
+    rc = shg_nms_candidates(d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, rows, cols, low, d_count, cap, d_list_idx,
+                            d_list_mag, stream);
+    if (rc) return rc;
+    // the count and the head of the list travel together: one round trip for the usual ~10^4 candidates
+    const uint32_t head = std::min(first_chunk, cap);
+    SHG_CHECK(cudaMemcpyAsync(h_count, d_count, 4, cudaMemcpyDeviceToHost, st));
+    SHG_CHECK(cudaMemcpyAsync(h_list_idx, d_list_idx, (size_t)head * 4, cudaMemcpyDeviceToHost, st));
+    SHG_CHECK(cudaMemcpyAsync(h_list_mag, d_list_mag, (size_t)head * 8, cudaMemcpyDeviceToHost, st));
+    SHG_CHECK(cudaStreamSynchronize(st));
+    const uint32_t have = std::min(*h_count, cap);
+    if (have > head) {
+        SHG_CHECK(cudaMemcpyAsync(h_list_idx + head, d_list_idx + head, (size_t)(have - head) * 4,
+                                  cudaMemcpyDeviceToHost, st));
+        SHG_CHECK(cudaMemcpyAsync(h_list_mag + head, d_list_mag + head, (size_t)(have - head) * 8,
+                                  cudaMemcpyDeviceToHost, st));
+        SHG_CHECK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ---- host helper: strict convex-hull vertices of integer points -------------
+// (scipy.spatial.ConvexHull(points).vertices as a SET, reference ellipse_to_circle.py:263: the
+// reference only asks which edge regions own a hull vertex.)  Andrew's monotone chain with an exact
+// 64-bit cross product; collinear points on a hull edge are not vertices, as in Qhull.
+extern "C" int shg_hull_vertices(const int64_t* h_xy, int64_t n, int64_t* h_vertex_index, int64_t* h_n_vertices) {
+    SHG_REQUIRE(h_xy && h_vertex_index && h_n_vertices && n >= 0, "shg_hull_vertices: bad arguments");
+    std::vector<int64_t> order((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        if (h_xy[2 * a] != h_xy[2 * b]) return h_xy[2 * a] < h_xy[2 * b];
+        if (h_xy[2 * a + 1] != h_xy[2 * b + 1]) return h_xy[2 * a + 1] < h_xy[2 * b + 1];
+        return a < b;
+    });
+    // duplicates: keep the first occurrence
+    std::vector<int64_t> uniq;
+    uniq.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t a = order[i];
+        if (!uniq.empty()) {
+            const int64_t b = uniq.back();
+            if (h_xy[2 * a] == h_xy[2 * b] && h_xy[2 * a + 1] == h_xy[2 * b + 1]) continue;
+        }
+        uniq.push_back(a);
+    }
+    const int64_t m = (int64_t)uniq.size();
+    if (m < 3) {
+        for (int64_t i = 0; i < m; ++i) h_vertex_index[i] = uniq[i];
+        *h_n_vertices = m;
+        return 0;
+    }
+    auto cross = [&](int64_t o, int64_t a, int64_t b) -> __int128 {
+        const __int128 ax = h_xy[2 * a] - h_xy[2 * o], ay = h_xy[2 * a + 1] - h_xy[2 * o + 1];
+        const __int128 bx = h_xy[2 * b] - h_xy[2 * o], by = h_xy[2 * b + 1] - h_xy[2 * o + 1];
+        return ax * by - ay * bx;
+    };
+    std::vector<int64_t> hull((size_t)(2 * m));
+    int64_t k = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        while (k >= 2 && cross(hull[k - 2], hull[k - 1], uniq[i]) <= 0) --k;
+        hull[k++] = uniq[i];
+    }
+    for (int64_t i = m - 2, t = k + 1; i >= 0; --i) {
+        while (k >= t && cross(hull[k - 2], hull[k - 1], uniq[i]) <= 0) --k;
+        hull[k++] = uniq[i];
+    }
+    --k;                                                            // the last point repeats the first
+    for (int64_t i = 0; i < k; ++i) h_vertex_index[i] = hull[i];
+    *h_n_vertices = k;
     return 0;
 }

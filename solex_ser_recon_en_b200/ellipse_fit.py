@@ -66,7 +66,9 @@ def _smooth(img, sigma):
     return ndi.gaussian_filter(img, sigma, mode='constant', cval=0.0, truncate=4.0)
 
 
-def canny_edges(image, sigma, low, high):
+def thin_edges(image, sigma, low):
+    """Canny up to and including the interpolated non-maximum suppression: (flat indices ascending,
+    magnitudes) of the thin-edge pixels with magnitude >= low -- the list csrc/limb.cu produces on the GPU."""
     image = np.asarray(image, dtype=np.float64)
     rows, cols = image.shape
     weight = _smooth(np.ones_like(image), sigma) + np.finfo(np.float64).eps
@@ -97,9 +99,15 @@ def canny_edges(image, sigma, low, high):
     plus = mag[ii + d2i, jj + d2j] * w + mag[ii + d1i, jj + d1j] * (1.0 - w)
     minus = mag[ii - d2i, jj - d2j] * w + mag[ii - d1i, jj - d1j] * (1.0 - w)
     with np.errstate(invalid='ignore'):
-        keep = (same | opp) & (plus <= m) & (minus <= m)
-    thin = np.zeros_like(mag)
-    thin[ii[keep], jj[keep]] = m[keep]
+        keep = (same | opp) & (plus <= m) & (minus <= m) & (m > 0)
+    return ii[keep] * cols + jj[keep], m[keep]
+
+
+def canny_edges(image, sigma, low, high):
+    image = np.asarray(image, dtype=np.float64)
+    flat, m = thin_edges(image, sigma, low)
+    thin = np.zeros(image.shape)
+    thin.ravel()[flat] = m
 
     weak = thin > 0
     labels, count = ndi.label(weak, np.ones((3, 3), bool))
@@ -146,16 +154,27 @@ def limb_points(image, sigma=2.0):
 
 
 # ---------------------------------------------------------------- ellipse fit
+_C1_INV = np.linalg.inv(np.array([[0., 0., 2.], [0., -1., 0.], [2., 0., 0.]]))
+
+
 def fit_ellipse(points):
     """Halir-Flusser direct least-squares ellipse through (row, col) points.
     Returns (centre, width, height, phi) in LsqEllipse.as_parameters() terms:
     `width` is the semi-axis lying at angle phi from the first coordinate axis."""
-    x, y = np.asarray(points, dtype=float).T
-    D1 = np.stack([x * x, x * y, y * y], axis=1)
-    D2 = np.stack([x, y, np.ones_like(x)], axis=1)
+    pts = np.asarray(points, dtype=float)
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    # design matrices [x^2, xy, y^2] and [x, y, 1] filled column by column (same values and layout as
+    # np.stack(..., axis=1), without its temporaries: this function runs twice on the critical path)
+    D1 = np.empty((len(x), 3))
+    np.multiply(x, x, out=D1[:, 0])
+    np.multiply(x, y, out=D1[:, 1])
+    np.multiply(y, y, out=D1[:, 2])
+    D2 = np.empty((len(x), 3))
+    D2[:, 0] = x
+    D2[:, 1] = y
+    D2[:, 2] = 1.0
     S1, S2, S3 = D1.T @ D1, D1.T @ D2, D2.T @ D2
-    C1 = np.array([[0., 0., 2.], [0., -1., 0.], [2., 0., 0.]])
-    M = np.linalg.inv(C1) @ (S1 - S2 @ np.linalg.inv(S3) @ S2.T)
+    M = _C1_INV @ (S1 - S2 @ np.linalg.inv(S3) @ S2.T)
     _, vec = np.linalg.eig(M)
     good = 4 * vec[0] * vec[2] - vec[1] ** 2 > 0
     a1 = vec[:, np.nonzero(good)[0]]
@@ -185,6 +204,21 @@ def ellipse_outline(center, width, height, phi, n_points=100):
                  center[1] + width * np.cos(t) * np.sin(phi) + height * np.sin(t) * np.cos(phi)]
 
 
+class _LazyOutline:
+    """The fitted ellipse as 100 points, computed when somebody looks at it (only the diagnostic plot does)."""
+
+    def __init__(self, *params):
+        self.params, self._pts = params, None
+
+    def __array__(self, dtype=None, copy=None):
+        if self._pts is None:
+            self._pts = ellipse_outline(*self.params)
+        return self._pts if dtype is None else self._pts.astype(dtype)
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+
 def two_step(points):
     """Fit, drop the points that lie well inside the first ellipse, refit, then
     relabel the axes so that |phi| <= pi/4 (reference ellipse_to_circle.py:62-91).
@@ -194,7 +228,7 @@ def two_step(points):
     resid = np.linalg.norm(mat @ (points - np.array(center)).T * height, axis=0) - 1
     kept = points[resid > -np.max(resid)]
     center, width, height, phi = fit_ellipse(kept)
-    outline = ellipse_outline(center, width, height, phi)
+    outline = _LazyOutline(center, width, height, phi)
     ratio = width / height
     for _ in range(2):
         if phi > math.pi / 4:
@@ -265,36 +299,82 @@ def _components(flat, cols):
     return int(count.value), labels.astype(np.int64)
 
 
-def limb_points_device(eng, sums, sigma=2.0):
+def _hull_vertices(x, y):
+    """Indices of the convex-hull vertices of integer points (the set scipy.spatial.ConvexHull(...).vertices
+    reports; raises like Qhull when the points do not span a plane).  Exact integer monotone chain in libshg:
+    Qhull took 1.4 ms on the ~1600 row ends of a config-5 limb, this takes ~20 us."""
+    import ctypes as C
+    from ._lib import call
+    xy = np.ascontiguousarray(np.stack([x, y], axis=1), dtype=np.int64)
+    out = np.empty(len(xy), dtype=np.int64)
+    m = C.c_int64(0)
+    call('shg_hull_vertices', xy.ctypes.data, len(xy), out.ctypes.data, C.byref(m))
+    if m.value < 3:
+        raise Exception('ERROR: the limb pixels found do not span an area (convex hull is degenerate)')
+    return out[:m.value]
+
+
+def limb_points_device(eng, sums, sigma=2.0, chained=None):
     """limb_points() with the image-sized work on the GPU.  `sums` is the int32
     (rows, cols) device tensor of 4x4 block sums; results are bit-identical to
     limb_points(sums * 2**-20) because every device step mirrors the operation
-    order of the library call it replaces (csrc/limb.cu)."""
+    order of the library call it replaces (csrc/limb.cu).
+
+    chained (default; SHG_LIMB_STEPWISE=1 selects the other): the threshold search runs as one queue of
+    kernels with its scalars kept on the device and two blocking read-backs in total; otherwise every
+    scalar is read back as soon as it exists (~15 round trips; the original formulation, kept as the
+    cross-check of the chained one)."""
+    import os
+    if chained is None:
+        chained = not os.environ.get('SHG_LIMB_STEPWISE')
     rows, cols = sums.shape
     n = rows * cols
     scale_img = 2.0 ** -20
-    fallback = 0.9 * (eng.sum_u32(sums) * scale_img) / (rows * cols)
     bw = int(rows * 0.01)
     scale = 1.0 / (bw * bw)
-    box = eng.box_sum_u32(sums, bw, bw)
+    s5 = 1.0 / 25
 
     def blurred(b, s):
         return (float(b) * scale_img) * s
 
     prev = int(np.floor((n - 1) * np.true_divide(99, 100)))
-    b_lo, b_hi = eng.select_u32(box, [prev, min(prev + 1, n - 1)])
-    ceiling = percentile_from_pair(blurred(b_lo, scale), blurred(b_hi, scale), n, 99)
-    r_lo, r_hi = eng.blur_range(box, scale, ceiling)
-    first, last = blurred(r_lo, scale), blurred(r_hi, scale)
-    if first == last:
-        first, last = first - 0.5, last + 0.5
-    edges = np.linspace(first, last, 21)
-    counts = eng.blur_hist(box, scale, ceiling, edges)
+    ranks = [prev, min(prev + 1, n - 1), (n - 1) // 2, n // 2]
+    if chained:
+        virtual = (n - 1) * np.true_divide(99, 100)
+        gamma = float(virtual - np.floor(virtual))
+        box, f = eng.limb_front(sums, bw, ranks, gamma)
+        b_lo, b_hi, m_lo, m_hi = f['stats']
+        ceiling = percentile_from_pair(blurred(b_lo, scale), blurred(b_hi, scale), n, 99)
+        r_lo, r_hi = f['range']
+        first, last = blurred(r_lo, scale), blurred(r_hi, scale)
+        if first == last:
+            first, last = first - 0.5, last + 0.5
+        edges = np.linspace(first, last, 21)
+        counts = f['counts']
+        if ceiling != f['ceiling'] or not np.array_equal(edges, f['edges']):
+            # the device's percentile interpolation / np.linspace disagrees with NumPy's in the last bit
+            # (never observed): redo the histogram with the host's numbers
+            r_lo, r_hi = eng.blur_range(box, scale, ceiling)
+            first, last = blurred(r_lo, scale), blurred(r_hi, scale)
+            if first == last:
+                first, last = first - 0.5, last + 0.5
+            edges = np.linspace(first, last, 21)
+            counts = eng.blur_hist(box, scale, ceiling, edges)
+        fallback = 0.9 * (f['total'] * scale_img) / (rows * cols)
+    else:
+        fallback = 0.9 * (eng.sum_u32(sums) * scale_img) / (rows * cols)
+        box = eng.box_sum_u32(sums, bw, bw)
+        b_lo, b_hi = eng.select_u32(box, ranks[:2])
+        ceiling = percentile_from_pair(blurred(b_lo, scale), blurred(b_hi, scale), n, 99)
+        r_lo, r_hi = eng.blur_range(box, scale, ceiling)
+        first, last = blurred(r_lo, scale), blurred(r_hi, scale)
+        if first == last:
+            first, last = first - 0.5, last + 0.5
+        edges = np.linspace(first, last, 21)
+        counts = eng.blur_hist(box, scale, ceiling, edges)
+        box5 = eng.box_sum_u32(sums, 5, 5)
+        m_lo, m_hi = eng.select_u32(box5, ranks[2:])
     level = flood_level(counts, edges, fallback)
-
-    box5 = eng.box_sum_u32(sums, 5, 5)
-    m_lo, m_hi = eng.select_u32(box5, [(n - 1) // 2, n // 2])
-    s5 = 1.0 / 25
     median = blurred(m_lo, s5) if n % 2 else np.mean([blurred(m_lo, s5), blurred(m_hi, s5)])
     low = median / 10
     high = low * 1.5
@@ -302,49 +382,68 @@ def limb_points_device(eng, sums, sigma=2.0):
         if sigma <= 0:
             raise Exception('ERROR: could not find any edges')
         with eng.stage('ellipse_fit:canny(device)'):
-            flat, mag = eng.canny_candidates(box, scale, level, gaussian_weights(sigma), low)
-        if len(flat):
-            count, lab = _components(flat, cols)
-            strong = np.zeros(count + 1, bool)
-            strong[np.unique(lab[mag >= high])] = True
-            keep = strong[lab]
-            flat_e = flat[keep]                                   # canny's edge pixels, raster order
-            if len(flat_e):
-                break
+            if chained:
+                flat, mag = eng.limb_canny(box, scale, level, gaussian_weights(sigma), low)
+            else:
+                flat, mag = eng.canny_candidates(box, scale, level, gaussian_weights(sigma), low)
+        sel = select_limb_pixels(flat, mag, high, cols)
+        if sel is not None:
+            return sel
         sigma -= 0.5
+
+
+def select_limb_pixels(flat, mag, high, cols):
+    """Host half of the limb search, on the sparse list of thin-edge pixels the device returns
+    (`flat` ascending flat indices, `mag` their gradient magnitudes): canny's hysteresis, the two largest
+    8-connected regions, the convex-hull test, the top / bottom crop (reference ellipse_to_circle.py:250-291).
+    Returns (kept (row, col) float points, all edge points) or None when canny leaves no edge."""
+    if not len(flat):
+        return None
+    count, lab = _components(flat, cols)
+    strong = np.zeros(count + 1, bool)
+    strong[lab[mag >= high]] = True
+    keep = strong[lab]
+    flat_e = flat[keep]                                       # canny's edge pixels, raster order
+    if not len(flat_e):
+        return None
     # labels of the surviving components, renumbered 1.. in raster order of their first pixel: what
     # scipy.ndimage.label(edges) would give (a component survives hysteresis whole, so its pixels and
     # the relative order of first pixels are unchanged)
-    kept_labels = np.flatnonzero(strong)
-    renum = np.zeros(count + 1, dtype=np.int64)
-    renum[kept_labels] = np.arange(1, len(kept_labels) + 1)
-    n_regions, lab = len(kept_labels), renum[lab[keep]]
+    renum = np.cumsum(strong)                                 # strong[0] is False: kept labels become 1..
+    n_regions = int(renum[-1])
+    lab = renum[lab[keep]]
     sizes = np.bincount(lab, minlength=n_regions + 1)
     sizes[0] = -1
-    ranked = sorted(sizes.tolist(), reverse=True)[:min(n_regions, NUM_REG)]
-    chosen = [sizes.tolist().index(s) for s in ranked]
-    sel = np.isin(lab, chosen)
+    # the reference picks labels by list.index of the sorted sizes: ties resolve to the lowest label (twice)
+    top = np.sort(sizes)[::-1][:min(n_regions, NUM_REG)]
+    chosen = [int(np.argmax(sizes == s_)) for s_ in top]
+    sel = lab == chosen[0]
+    for c in chosen[1:]:
+        sel |= lab == c
     flat_sel = flat_e[sel]
-    pts = np.stack([flat_sel // cols, flat_sel % cols], axis=1)
+    lab_sel = lab[sel]
+    rows_sel = flat_sel // cols
+    cols_sel = flat_sel - rows_sel * cols
     # hull vertices are extreme points, and every extreme point is the first or last pixel of its row:
     # the hull of those (<= 2 per row) has the same vertices as the hull of all points
-    row_start = np.flatnonzero(np.diff(pts[:, 0], prepend=-1))
-    row_last = np.append(row_start[1:] - 1, len(pts) - 1)
-    ends = np.unique(np.concatenate([row_start, row_last]))
-    hull_flat = flat_sel[ends[ConvexHull(pts[ends]).vertices]] if len(ends) >= 3 else \
-        flat_sel[ConvexHull(pts).vertices]
-    kept = np.zeros(len(flat_e), bool)
-    for c in chosen:
-        region = lab == c
-        if np.isin(flat_e[region], hull_flat).any():
-            kept |= region
-    lo, hi = pts[:, 0].min(), pts[:, 0].max()
+    first = np.empty(len(rows_sel), bool)
+    first[0] = True
+    np.not_equal(rows_sel[1:], rows_sel[:-1], out=first[1:])
+    last = np.empty(len(rows_sel), bool)
+    last[-1] = True
+    last[:-1] = first[1:]
+    ends = np.flatnonzero(first | last)
+    on_hull = ends[_hull_vertices(rows_sel[ends], cols_sel[ends])]
+    touching = np.unique(lab_sel[on_hull])                     # regions with a pixel among the hull vertices
+    lo, hi = int(rows_sel[0]), int(rows_sel[-1])               # raster order: first / last row of the selection
     span = hi - lo
     r_all = flat_e // cols
     band = (r_all >= int(lo + span * EDGE_CROP)) & (r_all < int(hi - span * EDGE_CROP))
+    kept = np.isin(lab, touching) if len(touching) > 1 else lab == touching[0]
     out = flat_e[kept & band]
-    return (np.stack([out // cols, out % cols], axis=1).astype(float),
-            np.stack([flat_e // cols, flat_e % cols], axis=1))
+    r_out = out // cols
+    return (np.stack([r_out, out - r_out * cols], axis=1).astype(float),
+            np.stack([r_all, flat_e - r_all * cols], axis=1))
 
 
 def fit_from_device(eng, sums):

@@ -109,22 +109,31 @@ def _ptr(t) -> int:
 
 
 class _Stage:
+    """One stage of the path: an NVTX range (always; free without a profiler attached) and, while
+    eng.profile_stages is set, a pair of CUDA events on the current stream plus the host times at which the
+    block was entered and left (stage timers / trace ranges)."""
+
     def __init__(self, eng, name):
         self.eng, self.name = eng, name
 
     def __enter__(self):
+        torch.cuda.nvtx.range_push('shg:' + self.name)
         if getattr(self.eng, 'profile_stages', False):
+            import time
+            self.h0 = time.perf_counter()
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record(torch.cuda.current_stream(self.eng.device))
         return self
 
     def __exit__(self, *exc):
-        if getattr(self.eng, 'profile_stages', False):
+        if getattr(self.eng, 'profile_stages', False) and hasattr(self, 'a'):
+            import time
             b = torch.cuda.Event(enable_timing=True)
             b.record(torch.cuda.current_stream(self.eng.device))
             if not hasattr(self.eng, '_stage_events'):
                 self.eng._stage_events = []
-            self.eng._stage_events.append((self.name, self.a, b))
+            self.eng._stage_events.append((self.name, self.a, b, self.h0, time.perf_counter()))
+        torch.cuda.nvtx.range_pop()
         return False
 
 
@@ -174,21 +183,23 @@ class Engine:
     def stage_report(self):
         torch.cuda.synchronize(self.device)
         out = {}
-        for name, a, b in getattr(self, '_stage_events', []):
+        for name, a, b, _, _ in getattr(self, '_stage_events', []):
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         self._stage_events = []
         return out
 
     def stage_timeline(self):
-        """[(name, start_ms, end_ms)] of the recorded stages relative to the first one (diagnostics:
-        which stages overlap, where the device idles).  Clears the record like stage_report()."""
+        """[(name, gpu start_ms, gpu end_ms, host enter_ms, host exit_ms)] of the recorded stages relative to
+        the first one (diagnostics: which stages overlap, where the device idles, where the host is late).
+        Clears the record like stage_report()."""
         torch.cuda.synchronize(self.device)
         ev = getattr(self, '_stage_events', [])
         self._stage_events = []
         if not ev:
             return []
-        base = ev[0][1]
-        return [(name, base.elapsed_time(a), base.elapsed_time(b)) for name, a, b in ev]
+        base, h = ev[0][1], ev[0][3]
+        return [(name, base.elapsed_time(a), base.elapsed_time(b), (h0 - h) * 1e3, (h1 - h) * 1e3)
+                for name, a, b, h0, h1 in ev]
 
     @property
     def stream(self) -> int:
@@ -475,6 +486,14 @@ class Engine:
         self.n_launches += 2
         return mm
 
+    def checksum(self, img) -> int:
+        """Position-sensitive 64-bit checksum of a contiguous uint16 device tensor (shg_checksum_u16)."""
+        assert img.is_contiguous() and img.dtype == torch.uint16
+        out = self.empty((1,), torch.int64)
+        call('shg_checksum_u16', img.data_ptr(), img.numel(), out.data_ptr(), self.stream)
+        self.n_launches += 1
+        return int(out.cpu().item()) & 0xFFFFFFFFFFFFFFFF
+
     def minmax(self, img):
         lo, hi = self.minmax_device(img)[0].cpu().tolist()
         return int(lo), int(hi)
@@ -612,6 +631,64 @@ class Engine:
         order = np.argsort(idx_h, kind='stable')
         return idx_h[order], mag_h[order]
 
+    def _limb_buffers(self, rows, cols):
+        """Scratch of the limb search for one image shape, allocated once (the search is on the critical
+        path of every multi-GPU step: no allocator calls, no pinned-memory registration per scan)."""
+        key = (rows, cols)
+        if getattr(self, '_limb_key', None) != key:
+            n = rows * cols
+            cap = 1 << 17
+            self._limb = dict(
+                u32=self.empty((3, rows, cols), torch.int32),            # box, box5, tmp
+                f64=self.empty((6, n), torch.float64),                   # smoothed, tmp0, tmp1, gi, gj, mag
+                state=self.empty((int(lib.shg_limb_state_bytes()),), torch.uint8),
+                count=self.empty((1,), torch.int32), cap=cap,
+                idx=self.empty((cap,), torch.int32), mag=self.empty((cap,), torch.float64),
+                h_idx=torch.empty((cap,), dtype=torch.int32, pin_memory=True),
+                h_mag=torch.empty((cap,), dtype=torch.float64, pin_memory=True),
+                h_cnt=torch.empty((1,), dtype=torch.int32, pin_memory=True))
+            self._limb_key = key
+        return self._limb
+
+    def limb_front(self, sums, bw: int, ranks4, gamma: float, n_bins: int = 20):
+        """The threshold search of the limb detection as one queue of kernels and ONE read-back
+        (shg_limb_front).  Returns (box, dict of exact host scalars)."""
+        rows, cols = sums.shape
+        L = self._limb_buffers(rows, cols)
+        bufs = L['u32']
+        r = (C.c_int64 * 4)(*[int(v) for v in ranks4])
+        out = (C.c_double * 80)()
+        call('shg_limb_front', sums.data_ptr(), rows, cols, int(bw), r, float(gamma), int(n_bins),
+             bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), L['state'].data_ptr(), out, self.stream)
+        self.n_launches += 17
+        res = dict(total=int(out[0]), stats=[int(out[1 + q]) for q in range(4)], ceiling=float(out[5]),
+                   range=(int(out[6]), int(out[7])), edges=np.array(out[8:9 + n_bins], dtype=np.float64),
+                   counts=np.array(out[41:41 + n_bins], dtype=np.float64).astype(np.int64))
+        return bufs[0], res
+
+    def limb_canny(self, box, scale: float, level: float, weights: np.ndarray, low: float):
+        """canny_candidates() with one round trip: (flat indices ascending, magnitudes)."""
+        rows, cols = box.shape
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        L = self._limb_buffers(rows, cols)
+        while True:
+            cap = L['cap']
+            call('shg_limb_canny', box.data_ptr(), rows, cols, float(scale), float(level),
+                 w.ctypes.data_as(C.POINTER(C.c_double)), len(w) - 1, float(np.finfo(np.float64).eps), float(low),
+                 L['f64'].data_ptr(), L['count'].data_ptr(), cap, L['idx'].data_ptr(), L['mag'].data_ptr(),
+                 min(cap, 1 << 15), L['h_cnt'].data_ptr(), L['h_idx'].data_ptr(), L['h_mag'].data_ptr(), self.stream)
+            self.n_launches += 7
+            m = int(L['h_cnt'].numpy().view(np.uint32)[0])
+            if m <= cap:
+                break
+            cap = 1 << int(m - 1).bit_length()                             # rare: a very long edge list
+            L.update(cap=cap, idx=self.empty((cap,), torch.int32), mag=self.empty((cap,), torch.float64),
+                     h_idx=torch.empty((cap,), dtype=torch.int32, pin_memory=True),
+                     h_mag=torch.empty((cap,), dtype=torch.float64, pin_memory=True))
+        idx_h = L['h_idx'].numpy()[:m].view(np.uint32).astype(np.int64)
+        order = np.argsort(idx_h)                                          # pixel indices are distinct
+        return idx_h[order], L['h_mag'].numpy()[:m][order]
+
     # ------------------------------------------------------- transversalium
     @property
     def logtab(self):
@@ -624,16 +701,25 @@ class Engine:
     @staticmethod
     def transversalium_chords(circle, borders):
         """Row range and per-row chord of correct_transversalium2 (solex_util.py:384-391)."""
-        cx, cy, rad = circle
-        y1 = math.ceil(max(cy - rad, borders[1]))
-        y2 = math.floor(min(cy + rad, borders[3]))
-        rows, xa, xb = [], [], []
-        for y in range(y1 + 1, y2):
-            dx = math.floor((rad ** 2 - (y - cy) ** 2) ** 0.5)
-            rows.append(y)
-            xa.append(math.ceil(max(cx - dx, borders[0])))
-            xb.append(math.floor(min(cx + dx, borders[2])))
-        return y1, y2, np.asarray(rows, np.int32), np.asarray(xa, np.int32), np.asarray(xb, np.int32)
+        cx, cy, rad = (float(v) for v in circle)
+        b0, b1, b2, b3 = (float(v) for v in borders)
+        y1 = math.ceil(max(cy - rad, b1))
+        y2 = math.floor(min(cy + rad, b3))
+        rows = np.arange(y1 + 1, max(y2, y1 + 1), dtype=np.int64)
+        # dx = floor((r^2 - (y - cy)^2) ** 0.5): vectorised with sqrt (the per-row Python loop cost 2-5 ms of host
+        # time, exposed whenever the GPU waits for the geometry); pow(x, 0.5) and sqrt(x) can differ in the last
+        # bit, which matters only within an ulp of an integer: those rows (there are normally none) are redone
+        # with the reference's own expression
+        arg = rad ** 2 - (rows.astype(np.float64) - cy) ** 2
+        with np.errstate(invalid='ignore'):
+            root = np.sqrt(arg)
+        near = ~(np.abs(root - np.rint(root)) > 1e-9 * np.maximum(1.0, np.abs(root)))     # also catches nan
+        for i in np.flatnonzero(near):
+            root[i] = (rad ** 2 - (float(rows[i]) - cy) ** 2) ** 0.5        # raises / complex like the reference
+        dx = np.floor(root)
+        xa = np.ceil(np.maximum(cx - dx, b0))
+        xb = np.floor(np.minimum(cx + dx, b2))
+        return y1, y2, rows.astype(np.int32), xa.astype(np.int32), xb.astype(np.int32)
 
     def transversalium_row_stats(self, imgs, rows, xa, xb, device: bool = False):
         """Per-row robust mean of log(img[y]/img[y-1]) over [xa, xb) (solex_util.py:392-395)

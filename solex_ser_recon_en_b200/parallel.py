@@ -49,6 +49,37 @@ def combine_stats(stack):
     return total_sum, total_max, stack.geom.n_frames
 
 
+_flag = {}
+
+
+def device_barrier():
+    """Rendezvous of the ranks' CURRENT STREAMS without blocking any host: a one-element NCCL all-reduce.
+    Kernels queued behind it on any rank start only after every rank's stream has reached it, so peer
+    stores issued before it (the row exchange inside the reconstruction kernel, the warp's stores into the
+    owners' images) are complete and visible to whatever is queued after it.  It replaces the
+    torch.cuda.synchronize() + dist.barrier() pairs of the first version of this module, each of which
+    drained the GPU and left it idle for a host round trip."""
+    _, size = world()
+    if size == 1:
+        return
+    dev = _comm_device()
+    t = _flag.get(dev)
+    if t is None:
+        t = _flag[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    if dev.type == 'cuda':
+        with get_engine().stage('rendezvous'):
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
+def _comm_device():
+    """Where collective payloads live: this rank's GPU under NCCL, host memory under gloo (CPU tests)."""
+    if dist.get_backend() == 'gloo':
+        return torch.device('cpu')
+    return get_engine().device
+
+
 def shift_owner(n_shifts: int, size: int | None = None, mode: str = 'by_shift'):
     """Rank that ends up holding the complete image of each shift.
     'by_shift': contiguous blocks of the shift list (index 0, the ellipse-fit
@@ -113,12 +144,17 @@ class RowExchange:
         self.images = raw.view(torch.uint16).view(max(1, len(self.mine)), n_frames, ih)
 
     def close(self):
-        from ._lib import lib
+        """Collective: every rank unmaps its peers' images, and only when ALL have done so does each rank
+        free its own allocation (freeing memory a peer still has mapped, or closing a mapping whose memory
+        the exporter already freed, leaves a CUDA error behind that the next checked call would report)."""
+        from ._lib import call
         for p in self.opened:
-            lib.shg_ipc_close(p)
+            call('shg_ipc_close', p)
         self.opened = []
+        if dist.is_initialized():
+            dist.barrier()
         if self.ptr:
-            lib.shg_ipc_free(self.ptr)
+            call('shg_ipc_free', self.ptr)
             self.ptr = 0
 
 
@@ -234,23 +270,22 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
         return [disk[i] for i in range(n_s)], mins, known
     g = stack.geom
     ex = row_exchange(n_s, g.n_frames, g.ih)
-    torch.cuda.synchronize()
-    dist.barrier()                         # owners are done reading the previous scan's images
+    device_barrier()                       # owners are done reading the previous scan's images
     if split:
         eng.recon(stack, fit, shifts[:1], out_ptrs=ex.ptrs[:1], k0_out=stack.k0, impl=1)
-        torch.cuda.synchronize()
-        dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
+        device_barrier()                   # every rank's rows of image 0 have landed on rank 0
+        ready = torch.cuda.Event()
+        ready.record()
         eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0, mins=mins[1:])
         known[1:] = [eng.recon_min_done] * (n_s - 1)
         if ex.owner[0] == rank:
-            first_done(ex.images[0], None)             # image 0 is complete (barrier above)
+            first_done(ex.images[0], ready)            # image 0 is complete once `ready` has passed
     else:
         eng.recon(stack, fit, shifts, out_ptrs=ex.ptrs, k0_out=stack.k0, mins=mins)
         known = [eng.recon_min_done] * n_s
-    # every rank tracked the minimum of its own frame rows (same kernel variant everywhere: same geometry)
+    # every rank tracked the minimum of its own frame rows (same kernel variant everywhere: same geometry);
+    # the all-reduce doubles as the rendezvous after which every rank's rows have landed
     dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-    torch.cuda.synchronize()
-    dist.barrier()                         # every rank's rows have landed
     out = [None] * n_s
     for n, j in enumerate(ex.mine):
         out[j] = ex.images[n]
@@ -306,16 +341,16 @@ def reconstruct_partial(stack, fit: np.ndarray, shifts, first_done=None):
     split = first_done is not None and n_s > 1
     if split:
         ex0 = row_exchange(1, n_frames, ih, mode='gather0', slot='first')
-        torch.cuda.synchronize()
-        dist.barrier()                     # rank 0 is done reading the previous scan's image
+        device_barrier()                   # rank 0 is done reading the previous scan's image
         eng.recon(stack, fit, shifts[:1], out_ptrs=ex0.ptrs[:1], k0_out=stack.k0, impl=1)
-        torch.cuda.synchronize()
-        dist.barrier()                     # every rank's rows of image 0 have landed on rank 0
+        device_barrier()                   # every rank's rows of image 0 have landed on rank 0
+        ready = torch.cuda.Event()
+        ready.record()
     eng.recon(stack, fit, shifts, disk=local, k0_out=h, mins=mins)
     if not eng.recon_min_done:             # kernel variant without minimum tracking: one pass over the local rows
         mins = eng.minmax_device(local[:, h:h + n_local])[:, 0].contiguous()
     if split and rank == 0:
-        first_done(ex0.images[0], None)
+        first_done(ex0.images[0], ready)
     _halo_exchange(local, h, n_local)
     # whole-image minimum and the two candidate [0][0] pixels (first / last frame, slit position 0): one all-reduce
     red = torch.zeros((3, n_s), dtype=torch.int32, device=eng.device)
@@ -361,10 +396,39 @@ def circ_exchange(n_imgs: int, out_rows: int, out_cols: int):
 
 
 def broadcast_object(obj, src: int):
-    """Small Python object from one rank to all (ellipse geometry)."""
+    """Small Python object from one rank to all."""
     _, size = world()
     if size == 1:
         return obj
     box = [obj]
     dist.broadcast_object_list(box, src=src)
     return box[0]
+
+
+def broadcast_geometry(geom, src: int = 0, error: BaseException | None = None):
+    """The ellipse geometry (circle (cx, cy, r), ratio, phi, borders [4]) from the rank that fitted it to
+    all: nine doubles and a status word in ONE NCCL broadcast of a device tensor (broadcast_object_list
+    pickles and costs two broadcasts and two host synchronisations).  If the fit failed on `src`
+    (`error`), every rank raises instead of waiting in a collective for a result that will not come."""
+    rank, size = world()
+    if size == 1:
+        if error is not None:
+            raise error
+        return geom
+    dev = _comm_device()
+    vals = np.zeros(10, dtype=np.float64)
+    if rank == src:
+        if error is None:
+            circle, ratio, phi, borders = geom
+            vals[:9] = [circle[0], circle[1], circle[2], ratio, phi] + [float(b) for b in borders]
+            vals[9] = 1.0
+        t = get_engine().upload(vals) if dev.type == 'cuda' else torch.from_numpy(vals)
+    else:
+        t = torch.empty((10,), dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=src)
+    v = t.cpu().numpy()
+    if v[9] != 1.0:
+        if error is not None:
+            raise error
+        raise ShgError('the ellipse fit failed on rank %d (see its traceback)' % src)
+    return (float(v[0]), float(v[1]), float(v[2])), float(v[3]), float(v[4]), [float(b) for b in v[5:9]]

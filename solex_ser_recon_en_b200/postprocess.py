@@ -135,10 +135,11 @@ def circularise_partial(parts, phi, ratio):
     (device_image.PartialImage, all slices of one local buffer) and stores the pixels it produces straight
     into the rank that owns the image (peer memory).  Returns a list with a row-major DeviceImage for the
     images this rank owns and None for the others; owners are assigned by position in the list."""
-    import torch.distributed as dist
     from . import parallel
     eng = get_engine()
     rank, size = parallel.world()
+    prep = eng.stage('circ_prep')
+    prep.__enter__()
     p0 = parts[0]
     ih, n_frames = p0.shape
     flip = p0.flip
@@ -164,13 +165,12 @@ def circularise_partial(parts, phi, ratio):
     mm[:, 1] = 65535
     cvals = red[2 if flip else 1][src].contiguous()                  # image[0][0]: last / first physical frame
     own_lo, own_hi = parallel.owned_logical_frames(n_frames, rank, size, flip)
-    torch.cuda.synchronize()
-    dist.barrier()                         # the owners are done reading the previous scan's circularised images
+    prep.__exit__()
+    parallel.device_barrier()              # the owners are done reading the previous scan's circularised images
     with eng.stage('warp'):
         eng.warp_batch(base, idx, flip, mat3, (oh, ow), mm, n_frames=n_frames, frame_origin=p0.k0 - p0.halo,
                        cvals=cvals, window=(own_lo, own_hi), out_ptrs=ex.ptrs_dev)
-    torch.cuda.synchronize()
-    dist.barrier()                         # every rank's pixels have landed
+    parallel.device_barrier()              # every rank's pixels have landed
     out = [None] * len(parts)
     for n, q in enumerate(ex.mine):
         out[q] = DeviceImage(eng, ex.images[n])
@@ -197,8 +197,9 @@ def detransversalium_many(images, circle, borders, strength):
     eng = get_engine()
     if not images:
         return [], np.zeros((0, 0))
-    batch = _stack_rows(eng, images)
-    y1, y2, rows, xa, xb = eng.transversalium_chords(circle, borders)
+    with eng.stage('transv_prep'):
+        batch = _stack_rows(eng, images)
+        y1, y2, rows, xa, xb = eng.transversalium_chords(circle, borders)
     with eng.stage('transv_stats'):
         stats = eng.transversalium_row_stats(batch, rows, xa, xb, device=True)
     h = batch.shape[1]

@@ -56,3 +56,29 @@ def test_label_points_matches_scipy_label():
         flat = np.flatnonzero(m)
         c2, l2 = E._components(flat, cols)
         assert c2 == cnt and np.array_equal(l2, lab.ravel()[flat]), t
+
+
+def test_hull_vertices_match_qhull():
+    """The host-side convex hull helper against scipy.spatial.ConvexHull on integer point sets: same vertex
+    SET (collinear points on an edge are not vertices in either), including limb-like thin rings."""
+    import numpy as np
+    from scipy.spatial import ConvexHull
+    from solex_ser_recon_en_b200 import ellipse_fit as E
+    rng = np.random.default_rng(1)
+    for t in range(120):
+        n = int(rng.integers(3, 400))
+        if t % 3 == 0:                                   # ring of pixels around an ellipse
+            ang = rng.uniform(0, 2 * np.pi, n)
+            pts = np.stack([200 + np.rint(150 * np.cos(ang)), 300 + np.rint(260 * np.sin(ang))], axis=1)
+        elif t % 3 == 1:                                 # small grid: many collinear and duplicate points
+            pts = rng.integers(0, 7, size=(n, 2)).astype(float)
+        else:
+            pts = rng.integers(-1000, 1000, size=(n, 2)).astype(float)
+        pts = pts.astype(np.int64)
+        try:
+            want = set(map(tuple, pts[ConvexHull(pts).vertices]))
+        except Exception:
+            continue                                     # Qhull refuses degenerate input
+        got = E._hull_vertices(pts[:, 0], pts[:, 1])
+        assert set(map(tuple, pts[got])) == want, t
+        assert len(got) == len(want), t

@@ -541,9 +541,10 @@ def test_limb_points_device_equals_host_pipeline(eng, shape, ry, rx, tilt):
     sums = eng.downscale4(fm, False)
     sums_h = sums.cpu().numpy()
     want_pts, want_raw = E.limb_points(sums_h.astype(np.float64) * 2.0 ** -20)
-    got_pts, got_raw = E.limb_points_device(eng, sums)
-    assert np.array_equal(got_raw, want_raw)
-    assert np.array_equal(got_pts, want_pts)
+    for chained in (True, False):          # one queue of kernels + 2 read-backs / the step-by-step formulation
+        got_pts, got_raw = E.limb_points_device(eng, sums, chained=chained)
+        assert np.array_equal(got_raw, want_raw), chained
+        assert np.array_equal(got_pts, want_pts), chained
     a = E.fit_from_block_sums(sums_h)
     b = E.fit_from_device(eng, sums)
     for x, y in zip(a[:4], b[:4]):
@@ -576,6 +577,42 @@ def test_limb_building_blocks(eng):
     lo, hi = eng.blur_range(box, scale, ceiling)
     assert ((lo * 2.0 ** -20) * scale, (hi * 2.0 ** -20) * scale) == (data.min(), data.max())
     assert np.array_equal(eng.blur_hist(box, scale, ceiling, edges), counts)
+    # the chained front end: the same numbers with the scalars kept on the device
+    n = s.size
+    prev = int(np.floor((n - 1) * 0.99))
+    ranks = [prev, prev + 1, (n - 1) // 2, n // 2]
+    virtual = (n - 1) * np.true_divide(99, 100)
+    box10, f = eng.limb_front(d, 10, ranks, float(virtual - np.floor(virtual)))
+    b10 = eng.box_sum_u32(d, 10, 10)
+    assert torch.equal(box10, b10)
+    sorted10 = np.sort(b10.cpu().numpy().view(np.uint32).ravel())
+    sorted5 = np.sort(box.cpu().numpy().view(np.uint32).ravel())
+    assert f['stats'] == [int(sorted10[ranks[0]]), int(sorted10[ranks[1]]), int(sorted5[ranks[2]]), int(sorted5[ranks[3]])]
+    assert f['total'] == int(s.astype(np.uint64).sum())
+    bl10 = (b10.cpu().numpy().view(np.uint32).astype(np.float64) * 2.0 ** -20) * (1.0 / 100)
+    ceil10 = np.percentile(bl10, 99)
+    assert f['ceiling'] == ceil10
+    data10 = bl10[bl10 < ceil10]
+    counts10, edges10 = np.histogram(data10, bins=20)
+    assert np.array_equal(f['edges'], edges10) and np.array_equal(f['counts'], counts10)
+    assert ((f['range'][0] * 2.0 ** -20) * 0.01, (f['range'][1] * 2.0 ** -20) * 0.01) == (data10.min(), data10.max())
+
+
+def test_checksum_is_position_sensitive_and_matches_the_formula(eng):
+    import torch
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 65536, size=(37, 1001)).astype(np.uint16)
+    idx = np.arange(a.size, dtype=np.uint64) + np.uint64(1)
+    with np.errstate(over='ignore'):
+        m = idx * np.uint64(0x9E3779B97F4A7C15)
+        m ^= m >> np.uint64(29)
+        want = int(((a.ravel().astype(np.uint64) + np.uint64(1)) * (m | np.uint64(1))).sum(dtype=np.uint64))
+    t = torch.from_numpy(a.view(np.int16)).to(eng.device).view(torch.uint16)
+    assert eng.checksum(t) == want
+    b = a.copy()
+    b[3, 5], b[3, 6] = a[3, 6], a[3, 5]
+    if b[3, 5] != a[3, 5]:
+        assert eng.checksum(torch.from_numpy(b.view(np.int16)).to(eng.device).view(torch.uint16)) != want
 
 
 @pytest.mark.parametrize('n,strength', [(3276, 301), (700, 301), (300, 301), (256, 301), (257, 9), (100, 301), (40, 301), (7, 301), (6, 5)])

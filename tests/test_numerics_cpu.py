@@ -101,3 +101,65 @@ def test_counting_select_model_is_exact_for_any_bin_edges():
         assert (b0, b1) == (d[t0], d[t1])
         if trial % 2 and trial % 3:
             assert m <= 256                                                # representative edges: short candidate list
+
+
+def test_limb_selection_on_the_sparse_list_equals_the_image_pipeline():
+    """ellipse_fit.select_limb_pixels (hysteresis, two largest regions, hull test, crop -- on the sparse list
+    of thin-edge pixels the GPU returns) gives the same points as limb_points() working on whole images
+    with scipy.ndimage.label, for a tilted ellipse, a Sun cut by the frame, and two separate arcs."""
+    import cv2
+    from solex_ser_recon_en_b200 import ellipse_fit as E
+    rng = np.random.default_rng(4)
+    for case in range(4):
+        rows, cols = 160 + 30 * case, 420 - 40 * case
+        yy, xx = np.mgrid[0:rows, 0:cols].astype(np.float64)
+        cy, cx = rows * (0.5 if case != 1 else 0.30), cols * 0.5
+        t = 0.1 * case
+        u = (yy - cy) * np.cos(t) + (xx - cx) * np.sin(t)
+        v = -(yy - cy) * np.sin(t) + (xx - cx) * np.cos(t)
+        rho2 = (u / (0.40 * rows)) ** 2 + (v / (0.42 * cols)) ** 2
+        img = np.where(rho2 < 1, 30000 * np.sqrt(np.clip(1 - 0.6 * rho2, 0, 1)), 500.0)
+        if case == 3:
+            img[:, cols // 2 - 6:cols // 2 + 6] = 500.0             # a dark lane: the limb breaks into two arcs
+        img = (img + 300 + rng.normal(0, 15, img.shape)) / 65536
+        want_pts, want_raw = E.limb_points(img)
+        flood = E.flood_image(img)
+        low = np.median(cv2.blur(img, ksize=(5, 5))) / 10
+        flat, mag = E.thin_edges(flood, 2.0, low)
+        got_pts, got_raw = E.select_limb_pixels(flat, mag, low * 1.5, cols)
+        assert np.array_equal(got_raw, want_raw), case
+        assert np.array_equal(got_pts, want_pts), case
+        assert len(got_pts) > 50
+
+
+def test_vectorised_chords_equal_the_reference_loop():
+    """Engine.transversalium_chords (vectorised) against the reference's per-row expressions
+    (solex_util.py:384-391), including circles whose chords end exactly on integers."""
+    import math
+    from solex_ser_recon_en_b200.engine import Engine
+
+    def loop(circle, borders):
+        y1 = math.ceil(max(circle[1] - circle[2], borders[1]))
+        y2 = math.floor(min(circle[1] + circle[2], borders[3]))
+        out = []
+        for y in range(y1 + 1, y2):
+            dx = math.floor((circle[2] ** 2 - (y - circle[1]) ** 2) ** 0.5)
+            out.append((y, math.ceil(max(circle[0] - dx, borders[0])), math.floor(min(circle[0] + dx, borders[2]))))
+        return y1, y2, np.asarray(out, dtype=np.int64).reshape(-1, 3)
+
+    rng = np.random.default_rng(11)
+    cases = [((1951.93, 2047.5, 1638.1), [313.02, 460.0, 3590.84, 3624.0]),
+             ((500.0, 400.0, 250.0), [0.0, 0.0, 1000.0, 800.0]),               # integer geometry: 3-4-5 rows hit integers
+             ((0, 0, 99999), [0, 120, 1220, 1100]),                            # the no-ellipse fallback
+             ((100.0, 100.0, 5.0), [0, 300, 200, 310])]                        # empty row range
+    for _ in range(40):
+        r = rng.uniform(20, 3000)
+        c = (rng.uniform(0, 4000), rng.uniform(0, 4000), r)
+        b = [c[0] - r * rng.uniform(0.5, 1.2), c[1] - r * rng.uniform(0.5, 1.2), c[0] + r * rng.uniform(0.5, 1.2),
+             c[1] + r * rng.uniform(0.5, 1.2)]
+        cases.append((c, b))
+    for circle, borders in cases:
+        y1, y2, want = loop(circle, borders)
+        g1, g2, rows, xa, xb = Engine.transversalium_chords(circle, borders)
+        assert (g1, g2) == (y1, y2)
+        assert np.array_equal(rows, want[:, 0]) and np.array_equal(xa, want[:, 1]) and np.array_equal(xb, want[:, 2])

@@ -66,6 +66,21 @@ def _worker(rank, world, port, out_dir):
         assert own[0] == 0 and own == sorted(own) and set(own) == set(range(world))
         geom = parallel.broadcast_object((1.5, [1, 2]) if rank == 0 else None, src=0)
         assert geom == (1.5, [1, 2])
+        # the ellipse geometry travels as one tensor broadcast; a failed fit on rank 0 raises on EVERY rank
+        parallel.device_barrier()
+        want = ((101.25, 2047.5, 1638.125), 0.195, -0.0125, [3.0, 460.0, 3590.84, 3624.0])
+        got = parallel.broadcast_geometry(want if rank == 0 else None, 0)
+        assert got == want, got
+        boom = ValueError('could not find any edges') if rank == 0 else None
+        try:
+            parallel.broadcast_geometry(None, 0, boom)
+        except ValueError:
+            assert rank == 0
+        except Exception as e:
+            assert rank != 0 and 'rank 0' in str(e)
+        else:
+            raise AssertionError('a failed fit must raise on every rank')
+        parallel.device_barrier()
         open(os.path.join(out_dir, 'ok%d' % rank), 'w').write('ok')
     finally:
         dist.destroy_process_group()

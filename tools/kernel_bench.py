@@ -98,6 +98,23 @@ def main():
         res['recon'] = dict(ms=ms, best_ms=best, GBps=recon_bytes / ms / 1e6, n_shifts=len(shifts), nb=nb)
     eng.recon(st, fit['fit'], shifts, disk=disk, k0_out=0)
     img_bytes = a.frames * geom.ih * 2
+    if want('limb'):
+        # the serial part of every multi-GPU step: limb search + ellipse fit of the first image, GPU otherwise idle
+        import time
+        from solex_ser_recon_en_b200 import ellipse_fit as E
+        for label, chained in (('chained', True), ('stepwise', False)):
+            ts = []
+            for rep in range(a.reps + 2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sums = eng.downscale4(disk[0], False)
+                pts, raw = E.limb_points_device(eng, sums, chained=chained)
+                t1 = time.perf_counter()
+                E.two_step(pts * 4)
+                t2 = time.perf_counter()
+                ts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+            ts = sorted(ts[2:])
+            res['limb_' + label] = dict(search_ms=ts[len(ts) // 2][0], two_step_ms=ts[len(ts) // 2][1], points=len(pts))
     if want('minmax'):
         ms, best = timed(lambda: eng.minmax(disk[1]), a.reps)
         res['minmax'] = dict(ms=ms, best_ms=best, GBps=img_bytes / ms / 1e6)
