@@ -173,12 +173,138 @@ def make_cpu_sample(a, n_sample):
     return synth.frames(spec, k0, k0 + n_sample)
 
 
+def synthetic_disk_image(a, seed=5):
+    """(ih, N) uint16 image with the statistics of a reconstructed config-5 disk (elliptical Sun, limb
+    darkening, texture, dust rows, pedestal, noise): the input of the post-processing half of the CPU arm."""
+    ih, n = a.width, a.frames
+    rng = np.random.default_rng(seed)
+    img = np.empty((ih, n), dtype=np.uint16)
+    k = np.arange(n, dtype=np.float64)
+    ck = ((k - n / 2) / (0.42 * n)) ** 2
+    dust = np.ones(ih)
+    dust[rng.integers(int(0.2 * ih), int(0.8 * ih), 12)] = 0.97
+    for r0 in range(0, ih, 256):
+        r = np.arange(r0, min(ih, r0 + 256), dtype=np.float64)
+        rho2 = ck[None, :] + (((r - ih / 2) / (0.40 * ih)) ** 2)[:, None]
+        disk = np.where(rho2 < 1.0, np.sqrt(np.maximum(1.0 - 0.6 * rho2, 0.0)), 0.02)
+        tex = 1.0 + 0.05 * np.sin(0.37 * k)[None, :] * np.cos(0.11 * r)[:, None]
+        sig = 7500.0 * disk * tex * dust[r0:r0 + len(r), None] + 300.0 + rng.normal(0.0, 50.0, size=rho2.shape)
+        img[r0:r0 + len(r)] = np.clip(np.rint(sig), 0, 65535).astype(np.uint16)
+    return img
+
+
+def run_unmodified_reference(a):
+    """CPU arm, kind "reference": the UNMODIFIED reference modules (oracle/_ref or /root/reference, loaded by
+    oracle/ref_shim) in ONE process with NumPy / OpenCV default threading, as the reference itself runs.
+
+    A full config-5 pass takes the reference ~20 min, so every step times a bounded sample of the same work
+    through the reference's own entry points and extrapolates (SURVEY 8d / BASELINE.md section 3):
+      read half    Solex_recon.solex_read on an n-frame excerpt of the scan (4096x512 frames, all 101 shifts):
+                   it scales with the frame count -> t_read * N / n;
+      process half Solex_recon.solex_process on one full-size (4096 x 20000) disk image: the ellipse fit runs
+                   once per scan (t_fit), circularisation + transversalium once per requested shift (t_image)
+                   -> t_fit + 101 * t_image.
+    image_process (CLAHE / PNG tail) is outside the metric and replaced by a no-op on this arm."""
+    import shutil
+    import tempfile
+
+    import cv2
+    from oracle import ref_shim
+    from solex_ser_recon_en_b200 import synth
+    ref = ref_shim.load()
+    cfg, shifts = workload_config(a)
+    n_shifts = len(shifts)
+    work = tempfile.mkdtemp(prefix='shg_ref_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    spec = synth.halpha(a.frames, a.width, a.height, seed=5)
+    spec.chunk = 8
+    disk = synthetic_disk_image(a)
+    timers = {}
+
+    def timed(fn, key):
+        def wrapper(*args, **kw):
+            t = time.perf_counter()
+            try:
+                return fn(*args, **kw)
+            finally:
+                timers[key] = timers.get(key, 0.0) + time.perf_counter() - t
+        return wrapper
+
+    real_e2c, real_ip = ref.Solex_recon.ellipse_to_circle, ref.Solex_recon.image_process
+    ref.Solex_recon.ellipse_to_circle = timed(real_e2c, 'fit')
+    ref.Solex_recon.image_process = lambda frame, cercle, options, header, basefich: (None, None)
+    state = {'n': 0, 'path': None}
+
+    def sample_file(n):
+        if state['n'] != n:
+            k0 = (a.frames - n) // 2
+            state['path'] = synth.write_ser_from_array(os.path.join(work, 'sample.SER'), synth.frames(spec, k0, k0 + n))
+            state['n'] = n
+        return state['path']
+
+    def one_step(n):
+        timers.clear()
+        opt = ref_shim.default_options(shift=list(shifts), output_dir=work)
+        t0 = time.perf_counter()
+        disk_list, bounds, hdr = ref.Solex_recon.solex_read(sample_file(n), opt)
+        t_read = time.perf_counter() - t0
+        del disk_list
+        # post-processing of ONE requested shift on a full-size image (index 0 = the ellipse-fit shift, index 1 =
+        # shift 0, exactly the list solex_read builds: Solex_recon.py:55)
+        opt2 = ref_shim.default_options(shift=[0], output_dir=work)
+        opt2.update(basefich0=os.path.join(work, 'sample'), shift_requested=[0], shift=[10, 0])
+        t1 = time.perf_counter()
+        ref.Solex_recon.solex_process(opt2, [disk, disk], (int(0.1 * a.width), int(0.9 * a.width)), hdr)
+        t_proc = time.perf_counter() - t1
+        t_fit = timers.get('fit', 0.0)
+        return t_read, t_fit, t_proc - t_fit
+
+    try:
+        budget = max(5.0, min(14.0, 270.0 / max(1, a.steps + a.warmup)))
+        t_read, t_fit, t_img = one_step(16)                        # calibration (untimed)
+        n = a.sample_frames or int(max(8, min(512, 16 * max(1.0, budget - t_fit - t_img) / max(t_read, 1e-3))))
+        wall, full = [], []
+        for it in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            t_read, t_fit, t_img = one_step(n)
+            if it >= a.warmup:
+                wall.append(time.perf_counter() - t0)
+                full.append(a.frames / n * t_read + t_fit + n_shifts * t_img)
+    finally:
+        ref.Solex_recon.ellipse_to_circle, ref.Solex_recon.image_process = real_e2c, real_ip
+        shutil.rmtree(work, ignore_errors=True)
+    t_full = float(np.mean(full))
+    value = a.frames / t_full
+    sample_desc = ('UNMODIFIED reference modules (%s), one process: per step solex_read on a %d-frame excerpt (%dx%d, %d '
+                   'shifts; last step %.2f s) + solex_process of one full-size %dx%d disk image (ellipse fit %.2f s, '
+                   'circularise + transversalium %.2f s per image); full scan = %d/%d x read + fit + %d x image = %.0f s; '
+                   'image_process (CLAHE / PNG, outside the metric) is a no-op; scikit-image / lsq-ellipse are not '
+                   'installable here: oracle/thirdparty.py NumPy restatements stand in for warp / canny / LsqEllipse' %
+                   ('oracle/_ref archive' if ref_shim.source() == 'staged' else '/root/reference', n, a.width, a.height,
+                    n_shifts, t_read, a.width, a.frames, t_fit, t_img, a.frames, n, n_shifts, t_full))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': a.gpus,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': 1e3 * float(np.mean(wall)), 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u16+f64', 'data': 'synthetic', 'config': cfg,
+        'extrapolated_full_scan_s': t_full,
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': 1, 'kind': 'reference', 'sample': sample_desc,
+                         'host_cpus': os.cpu_count(), 'cv2_threads': cv2.getNumThreads()},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def run_reference_arm(a):
     import concurrent.futures as cf
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    from oracle import ref_shim
+    if ref_shim.available() and not os.environ.get('SHG_REF_PORT'):
+        return run_unmodified_reference(a)
+    # fallback (kind "port"): the oracle's restatement of the read half on every host core
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 32))
     n_sample = a.sample_frames or 16 * workers
@@ -193,9 +319,9 @@ def run_reference_arm(a):
                 times.append(t)
     ms = 1e3 * float(np.mean(times))
     value = n_sample / (ms / 1e3)
-    sample_desc = ('%d frames of %dx%d at %d shifts per step through the oracle port of solex_read (mean/max, line '
-                   'detection + cubic fit, reconstruction); circularisation + transversalium (O(1) in frame count) '
-                   'not included, which favours the CPU arm' % (n_sample, a.width, a.height, len(shifts)))
+    sample_desc = ('oracle/_ref absent: %d frames of %dx%d at %d shifts per step through the oracle PORT of solex_read '
+                   '(mean/max, line detection + cubic fit, reconstruction); circularisation + transversalium (O(1) in '
+                   'frame count) not included, which favours the CPU arm' % (n_sample, a.width, a.height, len(shifts)))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',

@@ -4,9 +4,12 @@
 two absent numeric packages (scikit-image, lsq-ellipse) replaced by the
 restatements in oracle/thirdparty.py (parity unpinned for those call sites).
 
-/root/reference does not exist on the GPU box: this loader is used only by
-oracle/make_golden.py (fixture generation, run here) and by tests that are
-skipped when the reference tree is absent.  Nothing is copied from it.
+/root/reference does not exist on the GPU box.  There the loader falls back to
+oracle/_ref/reference_modules.zip -- the five modules, byte for byte, archived by
+oracle/stage_ref.py in a git-ignored directory that travels with the snapshot --
+so that bench.py's reference arm can time the unmodified reference on the box's
+host cores.  Used by oracle/make_golden.py (fixture generation, run here), by
+bench.py --impl reference, and by tests that are skipped when neither tree exists.
 """
 from __future__ import annotations
 
@@ -15,11 +18,21 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'reference_modules.zip')
 REFERENCE_DIR = os.environ.get('SHG_REFERENCE_DIR', '/root/reference')
+if not os.path.isfile(os.path.join(REFERENCE_DIR, 'solex_util.py')) and os.path.isfile(_STAGED):
+    REFERENCE_DIR = _STAGED                      # a zip archive on sys.path: Python imports the modules from it
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_DIR, 'solex_util.py'))
+    return os.path.isfile(REFERENCE_DIR) or os.path.isfile(os.path.join(REFERENCE_DIR, 'solex_util.py'))
+
+
+def source() -> str:
+    """'tree' (/root/reference itself), 'staged' (the oracle/_ref archive) or 'absent'."""
+    if not available():
+        return 'absent'
+    return 'staged' if os.path.isfile(REFERENCE_DIR) else 'tree'
 
 
 class _Anything:

@@ -37,7 +37,14 @@ def solex_do_work(tasks, flag_command_line=False):
     (Solex_recon.py:30-42).  Here file i+1 is ingested (pinned ring -> H2D on the ingest streams,
     the call releases the GIL) while one worker thread runs the GPU post-processing of file i and
     four more run the host tails (CLAHE + PNG / FITS)."""
-    with ThreadPoolExecutor(max_workers=1) as gpu_post, ThreadPoolExecutor(max_workers=4) as tails:
+    def on_engine_device():
+        # CUDA's current device is per host thread: the post-processing thread must use the engine's GPU
+        # (SHG_DEVICE / LOCAL_RANK), not device 0
+        import torch
+        torch.cuda.set_device(get_engine().device)
+
+    with ThreadPoolExecutor(max_workers=1, initializer=on_engine_device) as gpu_post, \
+            ThreadPoolExecutor(max_workers=4) as tails:
         posts = []
         for file, options in tasks:
             print('file %s is processing' % file)
@@ -118,6 +125,7 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         requested, circular, cercle0, borders = _circularise_owned(options, disk_list, shifts, basefich0)
     # 3. transversalium for all requested shifts (batched), then the host tail per image
     images = [circular[i] for i in requested]
+    plot_jobs = []
     if options['transversalium'] and images and all(isinstance(im, DeviceImage) for im in images) \
             and not options['save_fit']:
         if not cercle0 == (-1, -1, -1):
@@ -128,6 +136,15 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         detrans, gains = postprocess.detransversalium_many(images, circle, bord, options['trans_strength'])
         options['_transversalium_cache'] = gains[-1]
         options['_transversalium_gains'] = {shifts[i]: gains[j] for j, i in enumerate(requested)}
+        if not options['clahe_only'] and not options['protus_only']:
+            # the reference plots the correction of every requested shift (solex_util.py:482-488)
+            from .solex_util import _plot_gain
+            for j, i in enumerate(requested):
+                target = output_path(basefich0 + '_shift=' + str(shifts[i]) + '_transversalium_correction.png', options)
+                if _pool is not None:
+                    plot_jobs.append(_pool.submit(_plot_gain, gains[j].copy(), target))
+                else:
+                    _plot_gain(gains[j], target)
     else:
         detrans = None
     futures = []
@@ -138,7 +155,7 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         if _pool is not None:
             futures.append(res)
         write_complete(log, options)
-    return futures if _pool is not None else None
+    return futures + plot_jobs if _pool is not None else None
 
 
 def _circularise_owned(options, disk_list, shifts, basefich0):
@@ -163,9 +180,12 @@ def _circularise_owned(options, disk_list, shifts, basefich0):
             basefich = basefich0 + '_shift=' + str(shifts[0])
             plots = not options['clahe_only'] and not options['protus_only']
             try:
-                if plots and 0 in requested:
-                    # diagnostic figure wanted: the one-image path draws it
-                    circular[0], cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+                if plots:
+                    # diagnostic figure wanted (the reference draws `_ellipse_fit.png` for the ellipse-fit shift
+                    # whether or not that shift was requested, ellipse_to_circle.py:316-341): the one-image path
+                    fixed, cercle0, ratio_fit, phi, borders = ellipse_to_circle(disk_list[0], options, basefich)
+                    if 0 in requested:
+                        circular[0] = fixed
                 else:
                     fit = fit_geometry(disk_list[0], options, basefich)
                     cercle0, ratio_fit, phi, borders = fit['circle'], fit['ratio'], fit['phi'], fit['borders']

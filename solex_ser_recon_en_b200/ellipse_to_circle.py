@@ -152,12 +152,24 @@ def ellipse_to_circle(image, options, basefich):
 
 
 def _plot_fit(image, fixed, raw, kept, outline, borders, path):
-    try:
-        import matplotlib.figure
-        import matplotlib.pyplot
-    except Exception:
-        return                                                                # diagnostic plot only
+    """`_ellipse_fit.png` (ellipse_to_circle.py:316-341): edges found, edges kept + fitted ellipse, corrected image."""
+    from . import miniplot
     image, fixed = np.asarray(image), np.asarray(fixed)
+    outline = np.asarray(outline)
+    if not miniplot.have_matplotlib():
+        import os
+        import cv2
+        tmp = [path + '.%d.png' % i for i in range(3)]
+        miniplot.image_overlay(tmp[0], image, np.asarray(raw)[:, ::-1], title='edge detection')
+        miniplot.image_overlay(tmp[1], image, np.asarray(kept)[:, ::-1], outline[:, ::-1], title='filtered edges / ellipse fit')
+        miniplot.image_overlay(tmp[2], fixed, hlines=(borders[1], borders[3]), vlines=(borders[0], borders[2]),
+                               title='geometrically corrected image')
+        miniplot.panels(path, [cv2.imread(t) for t in tmp])
+        for t in tmp:
+            os.remove(t)
+        return
+    import matplotlib.figure
+    import matplotlib.pyplot
     fig = matplotlib.figure.Figure()
     ax = [[fig.add_subplot(2, 2, 1), fig.add_subplot(2, 2, 2)], [fig.add_subplot(2, 2, 3), fig.add_subplot(2, 2, 4)]]
     fig.tight_layout()

@@ -86,10 +86,12 @@ class _Resident:
     key = None
     stack = None
     stats = None
+    owner = None              # the reader object itself for readers without a file identity: keeps it alive, so
+    #                           that id() cannot be reused by another reader while its stack is cached
 
     @classmethod
     def drop(cls):
-        cls.key = cls.stack = cls.stats = None
+        cls.key = cls.stack = cls.stats = cls.owner = None
 
 
 def _reader_key(rdr):
@@ -112,7 +114,8 @@ def resident_stack(rdr, accumulate=True) -> DeviceStack:
                 eng.accumulate(rdr.stack, reset=True)
         return rdr.stack
     key = _reader_key(rdr)
-    if _Resident.key == key and _Resident.stack is not None and (_Resident.stack.accumulated or not accumulate):
+    if _Resident.key == key and _Resident.stack is not None and (_Resident.stack.accumulated or not accumulate) \
+            and (key[0] != 'object' or _Resident.owner is rdr):
         return _Resident.stack
     _Resident.drop()
     from . import parallel
@@ -154,6 +157,7 @@ def resident_stack(rdr, accumulate=True) -> DeviceStack:
         k0, k1 = parallel.frame_range(frames.shape[0])
         stack = eng.ingest_array(frames[k0:k1], n_total=frames.shape[0], k0=k0, accumulate=accumulate)
     _Resident.key, _Resident.stack, _Resident.stats = key, stack, stats
+    _Resident.owner = rdr if key[0] == 'object' else None
     return stack
 
 
@@ -208,9 +212,11 @@ def compute_mean_return_fit(vid_rdr, options, hdr, iw, ih, basefich0):
     eng, stack, mean_dev, max_dev = _mean_max_device(vid_rdr, options, basefich0)
     mean_early = eng.download_early(mean_dev)         # copied to the host underneath the line detection
     mean_img = mean_early.result() if options['save_fit'] or options['flag_display'] else None
-    if options['save_fit']:
+    from . import parallel
+    writer = parallel.world()[0] == 0                  # several ranks compute the same mean frame: one of them writes it
+    if options['save_fit'] and writer:
         fits.PrimaryHDU(mean_img, header=hdr).writeto(output_path(basefich0 + '_mean.fits', options), overwrite='True')
-    if options['flag_display']:
+    if options['flag_display'] and writer:
         cv2.namedWindow('Ser mean', cv2.WINDOW_NORMAL)
         cv2.imshow('Ser mean', mean_img)
         if cv2.waitKey(2000) == 27:
@@ -227,23 +233,27 @@ def compute_mean_return_fit(vid_rdr, options, hdr, iw, ih, basefich0):
     p = lf['p3']
     logme(basefich0 + '_log.txt', options, 'Spectral line polynomial fit: ' + str(p))
     fit = lf['fit']
-    if not options['clahe_only'] and not options['protus_only']:
+    if not options['clahe_only'] and not options['protus_only'] and writer:
         _plot_line_fit(mean_img, det, lf, y1, y2, output_path(basefich0 + '_spectral_line_data.png', options))
     return mean_img, fit, y1, y2
 
 
 def _plot_line_fit(mean_img, det, lf, y1, y2, path):
-    try:
-        import matplotlib.figure
-        import matplotlib.pyplot
-    except Exception:
-        return                                                   # diagnostic plot only; matplotlib is optional here
+    """`_spectral_line_data.png` (solex_util.py:263-273): the mean frame with the detected line minima and the fit."""
+    from . import miniplot
     sharp = det['min_sharp'].cpu().numpy()[y1:y2]
     good = lf['mask_good'].cpu().numpy().astype(bool)
+    s = (y2 - y1) // 20 + 1
+    if not miniplot.have_matplotlib():
+        pts = np.stack([sharp[good][::s], np.arange(y1, y2)[good][::s]], axis=1)
+        curve = np.stack([lf['fit'][:, 3], np.arange(mean_img.shape[0])], axis=1)
+        miniplot.image_overlay(path, mean_img, pts, curve, title='line detection (red) / polynomial fit (blue)')
+        return
+    import matplotlib.figure
+    import matplotlib.pyplot
     fig = matplotlib.figure.Figure()
     ax = fig.add_subplot(1, 1, 1)
     ax.imshow(mean_img, cmap=matplotlib.pyplot.cm.gray)
-    s = (y2 - y1) // 20 + 1
     ax.plot(sharp[good][::s], np.arange(y1, y2)[good][::s], 'rx', label='line detection')
     ax.plot(lf['fit'][:, 3], np.arange(mean_img.shape[0]), label='polynomial fit')
     ax.legend(loc='center left', bbox_to_anchor=(1, 0.5))
@@ -408,10 +418,12 @@ def correct_transversalium2(img, circle, borders, options, reqFlag, basefich):
 
 
 def _plot_gain(c, path):
-    try:
-        import matplotlib.figure
-    except Exception:
+    """`_transversalium_correction.png` (solex_util.py:482-488): the per-row correction factor."""
+    from . import miniplot
+    if not miniplot.have_matplotlib():
+        miniplot.line_plot(path, c, 'y', 'transversalium correction factor')
         return
+    import matplotlib.figure
     fig = matplotlib.figure.Figure()
     ax = fig.add_subplot(1, 1, 1)
     ax.plot(c)
