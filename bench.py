@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--timeline', action='store_true', help='print the stage timeline of one extra resident pass (stderr)')
     ap.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
+    ap.add_argument('--no-configs', action='store_true', help='skip the small-configuration lines (config_lines)')
     ap.add_argument('--record-crc', action='store_true',
                     help='store this run\'s outputs_crc in profiles/outputs_crc.json as the expected value (run at N=1)')
     return ap.parse_args()
@@ -334,6 +335,85 @@ def run_reference_arm(a):
     return 0
 
 
+# ===================================================== the other BASELINE configurations
+def config_lines(eng, max_files=16):
+    """BASELINE.json configs[0..3] at full size through the command line front end (SHG_MAIN.main, scan files on
+    tmpfs, `-c`: CLAHE + one PNG per image written): wall time of the whole invocation, frames/s, the file ->
+    pinned ring -> HBM ingest rate and how often the pinned ring was reused instead of reallocated.  These are
+    the parity-test configurations (tests/test_gpu_cli_configs.py checks them against the oracle); the lines put
+    their timings into the driver's record."""
+    import shutil
+    import tempfile
+
+    import cv2
+    from solex_ser_recon_en_b200 import SHG_MAIN, synth
+    from solex_ser_recon_en_b200.engine import ScanGeometry
+    base = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+    free = shutil.disk_usage(base).free
+    work = tempfile.mkdtemp(prefix='shg_cfg_', dir=base)
+    os.environ['SHG_NO_CONFIG'] = '1'
+    out = []
+
+    def device_payload(n, w, h, bpp, seed):
+        st = eng.synth_stack(ScanGeometry(w, h, bpp, n), seed=seed)
+        host = st.frames.cpu().numpy()
+        del st
+        return host
+
+    def ser(name, n, w, h, seed):
+        p = os.path.join(work, name)
+        with open(p, 'wb') as f:
+            f.write(synth.ser_header(w, h, 16, n))
+            f.write(device_payload(n, w, h, 2, seed).tobytes())
+        return p
+
+    def run(label, flags, files, frames, payload_bytes, reps=2):
+        best = None
+        for _ in range(reps):
+            SHG_MAIN.options.update(shift=[0], ratio_fixe=None, slant_fix=None, flip_x=False, crop_width_square=False,
+                                    clahe_only=False, save_fit=False, fixed_width=None, output_dir=work)
+            n_log, c0, r0 = len(eng.ingest_log), eng.ring_creates, eng.ring_reuses
+            t0 = time.perf_counter()
+            rc = SHG_MAIN.main(flags + files)
+            wall = time.perf_counter() - t0
+            assert rc == 0
+            ing = [st for _, st in eng.ingest_log[n_log:]]
+            rec = {'config': label, 'flags': ' '.join(flags), 'files': len(files), 'frames': frames, 'wall_s': round(wall, 4),
+                   'frames_per_s': round(frames / wall, 1), 'payload_GB': round(payload_bytes / 1e9, 3),
+                   'file_to_hbm_GBps': round(sum(s[2] for s in ing) / max(1e-9, sum(s[0] for s in ing)) / 1e9, 2)
+                   if ing else None,
+                   'pinned_ring_allocations': eng.ring_creates - c0, 'pinned_ring_reuses': eng.ring_reuses - r0}
+            if best is None or rec['wall_s'] < best['wall_s']:
+                best = rec
+        out.append(best)
+
+    try:
+        f1 = ser('cfg1.SER', 1000, 1280, 200, 1)
+        run('configs[0]: 16-bit SER 1000 x 1280x200, shift 0', ['-c'], [f1], 1000, 1000 * 1280 * 200 * 2)
+        os.remove(f1)
+        f2 = os.path.join(work, 'cfg2.avi')
+        pay = device_payload(2000, 1920, 256, 1, 2).reshape(2000, 256, 1920)
+        vw = cv2.VideoWriter(f2, 0, 25.0, (1920, 256), isColor=False)
+        for fr in pay:
+            vw.write(fr)
+        vw.release()
+        del pay
+        run('configs[1]: 8-bit AVI 2000 x 1920x256, mirror X + crop square', ['-cms'], [f2], 2000, 2000 * 1920 * 256)
+        os.remove(f2)
+        f3 = ser('cfg3.SER', 4000, 2048, 300, 3)
+        run('configs[2]: 16-bit SER 4000 x 2048x300, -w-10:10:1 (21 shifts)', ['-cw-10:10:1'], [f3], 4000,
+            4000 * 2048 * 300 * 2)
+        os.remove(f3)
+        per_file = 3000 * 2048 * 256 * 2
+        n_files = int(max(2, min(max_files, (free * 0.7 - 2e9) // per_file)))
+        f4 = [ser('cfg4_%02d.SER' % i, 3000, 2048, 256, 40 + i) for i in range(n_files)]
+        run('configs[3]: %d x 16-bit SER 3000 x 2048x256 back to back (one invocation)' % n_files, ['-c'], f4,
+            3000 * n_files, per_file * n_files, reps=1 if n_files > 4 else 2)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
 # ============================================================ output checksum
 CRC_FILE = os.path.join(ROOT, 'profiles', 'outputs_crc.json')
 
@@ -554,6 +634,19 @@ def run_b200(a):
     clocks = sampler.window(*dev['wall']) if sampler else None
     if sampler:
         sampler.stop()
+    config_results = None
+    if world == 1 and not a.no_configs and not cfg.get('reduced'):
+        del stack
+        results.clear()
+        release_resident()
+        torch.cuda.empty_cache()
+        import contextlib
+        import io
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):          # the CLI prints per-file progress lines
+                config_results = config_lines(eng)
+        except Exception as e:                                       # never lose the main line to a side measurement
+            config_results = [{'error': repr(e)}]
 
     if rank == 0:
         peaks = {}
@@ -612,6 +705,8 @@ def run_b200(a):
             line['e2e']['outputs_crc'] = e2e['crc']
         if world == 1 and not a.no_cpu:
             line['cpu_baseline'] = cpu_baseline_subprocess(a)
+        if config_results is not None:
+            line['config_lines'] = config_results
         print(json.dumps(line))
         sys.stdout.flush()
         if match is False or (e2e is not None and e2e['crc'] != dev['crc']):

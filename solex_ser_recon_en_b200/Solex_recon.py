@@ -86,6 +86,7 @@ def solex_read_reader(rdr, options, basefich0):
     finally:
         options.pop('_prefetch_fit', None)
     hdr['NAXIS1'] = iw
+    observer = options.get('_observer')                        # tests / diagnostics: see the seams of a CLI run
     for i in range(len(disk_list)):
         if disk_list[i] is None:                              # image owned by another rank
             continue
@@ -96,6 +97,8 @@ def solex_read_reader(rdr, options, basefich0):
             basefich = basefich0 + '_shift=' + str(options['shift'][i])
             fits.PrimaryHDU(np.asarray(disk_list[i]), header=hdr).writeto(
                 output_path(basefich + '_raw.fits', options), overwrite='True')
+    if observer is not None:
+        observer('disks', basefich0, disk_list)
     return disk_list, (backup_y1, backup_y2), hdr
 
 
@@ -148,8 +151,13 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
     else:
         detrans = None
     futures = []
+    observer = options.get('_observer')
     for j, i in enumerate(requested):
         basefich = basefich0 + '_shift=' + str(shifts[i])
+        if observer is not None:
+            observer('circular', basefich, images[j])
+            if detrans is not None:
+                observer('detrans', basefich, detrans[j])
         res = single_image_process(images[j], hdr, options, cercle0, borders, basefich, backup_bounds, _pool=_pool,
                                    _detrans=None if detrans is None else detrans[j])
         if _pool is not None:
@@ -274,6 +282,8 @@ def single_image_process(frame_circularized, hdr, options, cercle0, borders, bas
                 [0, backup_bounds[0] + 20, frame_circularized.shape[1] - 1, backup_bounds[1] - 20], options, 0, basefich)
     else:
         detrans = frame_circularized
+    if _detrans is None and options.get('_observer') is not None:
+        options['_observer']('detrans', basefich, detrans)
     sink = options.get('_result_sink')
     if sink is not None:                                      # callers that want the hot-path result itself
         return sink(basefich, detrans, cercle0)

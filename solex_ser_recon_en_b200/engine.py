@@ -172,6 +172,9 @@ class Engine:
         self._ingest = None
         self._ingest_cfg = None
         self.n_launches = 0            # kernels launched through this engine (bench's gpu_launches)
+        self.ring_creates = 0          # pinned ingest rings allocated / reused without reallocation
+        self.ring_reuses = 0
+        self.ingest_log = []           # (kind, (seconds, seconds waiting for reads, bytes, chunks)) of every ingest
 
     # ------------------------------------------------------------------ util
     def stage(self, name):
@@ -254,8 +257,10 @@ class Engine:
     def _ring(self, slot_bytes, n_slots, n_threads):
         cfg = (int(slot_bytes), int(n_slots), int(n_threads))
         if self._ingest is not None and self._ingest_cfg == cfg:
+            self.ring_reuses += 1                     # pinned slots reused by the next scan (batch mode)
             return self._ingest
         self.close_ring()
+        self.ring_creates += 1
         h = C.c_void_p()
         call('shg_ingest_create', self.index, cfg[0], cfg[1], cfg[2], C.byref(h))
         self._ingest, self._ingest_cfg = h, cfg
@@ -299,6 +304,7 @@ class Engine:
              _ptr(stack.sum) if accumulate else 0, _ptr(stack.max) if accumulate else 0, stats)
         stack.accumulated = bool(accumulate)
         self.n_launches += int(stats[3]) if accumulate else 0
+        self.ingest_log.append(('file', tuple(stats)))
         return stack, tuple(stats)
 
     def ingest_host(self, host_ptr: int, geom: ScanGeometry, n: int, k0: int = 0, frame_stride: int | None = None,
@@ -315,6 +321,7 @@ class Engine:
              _ptr(stack.sum) if accumulate else 0, _ptr(stack.max) if accumulate else 0, stats)
         stack.accumulated = bool(accumulate)
         self.n_launches += int(stats[3]) if accumulate else 0
+        self.ingest_log.append(('memory', tuple(stats)))
         return stack, tuple(stats)
 
     def ingest_array(self, frames: np.ndarray, n_total: int | None = None, k0: int = 0, accumulate: bool = True):

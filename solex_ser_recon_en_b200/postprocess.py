@@ -158,7 +158,15 @@ def circularise_partial(parts, phi, ratio):
         idx.append(off // stride)
     base = torch.as_strided(first, (max(idx) + 1, n_ext, ih), (stride, ih, 1))
     mins, red = p0.min_ref[0], p0.cval_ref[0]
-    src = eng.upload(np.asarray([p.min_ref[1] for p in parts], dtype=np.int64))
+    # Launch order of the images (blockIdx.z): every rank starts with the images of the NEXT rank and goes round,
+    # so that at any moment the ranks store into different owners.  In list order all ranks wrote into rank 0's
+    # memory first, then all into rank 1's, ...: the owner's NVLink ingress was the bottleneck and everybody
+    # else's egress idled (measured at four GPUs: 3.6 - 4.1 ms for this launch instead of 1.7).
+    order = sorted(range(len(parts)), key=lambda q: ((ex.owner[q] - rank - 1) % size, q))
+    if getattr(ex, 'ptrs_rot', None) is None:
+        ex.ptrs_rot = eng.upload(ex.ptrs.view(np.int64)[order]).view(torch.int64)
+    idx = [idx[q] for q in order]
+    src = eng.upload(np.asarray([parts[q].min_ref[1] for q in order], dtype=np.int64))
     assert all(p.min_ref[0].data_ptr() == mins.data_ptr() and p.cval_ref[0].data_ptr() == red.data_ptr() for p in parts)
     mm = torch.empty((len(parts), 2), dtype=torch.int32, device=eng.device)
     mm[:, 0] = mins[src]
@@ -169,7 +177,7 @@ def circularise_partial(parts, phi, ratio):
     parallel.device_barrier()              # the owners are done reading the previous scan's circularised images
     with eng.stage('warp'):
         eng.warp_batch(base, idx, flip, mat3, (oh, ow), mm, n_frames=n_frames, frame_origin=p0.k0 - p0.halo,
-                       cvals=cvals, window=(own_lo, own_hi), out_ptrs=ex.ptrs_dev)
+                       cvals=cvals, window=(own_lo, own_hi), out_ptrs=ex.ptrs_rot)
     parallel.device_barrier()              # every rank's pixels have landed
     out = [None] * len(parts)
     for n, q in enumerate(ex.mine):
