@@ -50,6 +50,11 @@ int shg_device_info(int device, int64_t* out6);
 int shg_accumulate(const void* d_frames, int bytes_per_px, int64_t n_frames, int64_t frame_px,
                    uint64_t* d_sum, uint32_t* d_max, void* stream);
 
+/* d_out[k] = sum of the raw pixels of frame k (file units): all_video_reader.means[k] = scale * d_out[k] / frame_px
+ * exactly as np.mean(frame) gives it (reference video_reader.py:143-147; integer sums below 2^53 are exact). */
+int shg_frame_sums(const void* d_frames, int bytes_per_px, int64_t n_frames, int64_t frame_px,
+                   uint64_t* d_out, void* stream);
+
 /* mean = floor(scale*sum / n_total), max = scale*max (scale = 256 for 8-bit
  * input: reference video_reader.py:121-122), written in IMAGE orientation
  * (ih x iw, rotated when W > H) as uint16. */

@@ -35,8 +35,24 @@ def solex_do_work(tasks, flag_command_line=False):
 
     The reference overlaps "read file i+1" with "post-process file i" through a process pool
     (Solex_recon.py:30-42).  Here file i+1 is ingested (pinned ring -> H2D on the ingest streams,
-    the call releases the GIL) while one worker thread runs the GPU post-processing of file i and
-    four more run the host tails (CLAHE + PNG / FITS)."""
+    the call releases the GIL) while one worker thread runs the transversalium correction and the
+    device -> host copies of file i and four more run the host tails (CLAHE + PNG / FITS)."""
+    def opened():
+        for file, options in tasks:
+            print('file %s is processing' % file)
+            yield video_reader(file), options, os.path.splitext(file)[0]
+    solex_do_work_readers(opened())
+
+
+def solex_do_work_readers(tasks):
+    """solex_do_work on already opened readers: `tasks` yields (reader, options, basefich0).
+
+    Pipeline (any number of GPUs): the calling thread runs solex_read of scan i+1 -- and the part of
+    solex_process that contains collectives (ellipse geometry, circularisation) -- while a worker thread finishes
+    scan i (transversalium, device -> host copies, hand-over to the host tails).  The worker issues no collective,
+    so the ranks' collective order is the calling threads' order; before scan i+1 reconstructs into buffers that
+    scan i's owners may still be reading, the caller waits for the worker to have finished scan i
+    (options['_before_recon'])."""
     def on_engine_device():
         # CUDA's current device is per host thread: the post-processing thread must use the engine's GPU
         # (SHG_DEVICE / LOCAL_RANK), not device 0
@@ -46,15 +62,12 @@ def solex_do_work(tasks, flag_command_line=False):
     with ThreadPoolExecutor(max_workers=1, initializer=on_engine_device) as gpu_post, \
             ThreadPoolExecutor(max_workers=4) as tails:
         posts = []
-        for file, options in tasks:
-            print('file %s is processing' % file)
-            disk_list, backup_bounds, hdr = solex_read(file, options)
-            if parallel.world()[1] > 1:
-                # collectives must be issued in the same order on every rank: no second thread
-                for fut in solex_process(options, disk_list, backup_bounds, hdr, tails):
-                    fut.result()
-            else:
-                posts.append(gpu_post.submit(solex_process, options, disk_list, backup_bounds, hdr, tails))
+        for rdr, options, basefich0 in tasks:
+            previous = posts[-1] if posts else None
+            options['_before_recon'] = (lambda p=previous: p.result()) if previous is not None else None
+            disk_list, backup_bounds, hdr = solex_read_reader(rdr, options, basefich0)
+            options.pop('_before_recon', None)
+            posts.append(solex_process(options, disk_list, backup_bounds, hdr, tails, _defer=gpu_post))
             del disk_list
         for post in posts:
             for fut in post.result():
@@ -102,11 +115,13 @@ def solex_read_reader(rdr, options, basefich0):
     return disk_list, (backup_y1, backup_y2), hdr
 
 
-def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
+def solex_process(options, disk_list, backup_bounds, hdr, _pool=None, _defer=None):
     """Circularise, de-transversalium, crop and write every requested shift
     (Solex_recon.py:93-133).  With `_pool` the host tail of each image is
     submitted to it and the futures are returned; otherwise it runs inline and
-    the return value is None like the reference's."""
+    the return value is None like the reference's.  With `_defer` (an executor) everything after the
+    circularisation -- which holds the only collectives -- runs there and a future of the tail futures is
+    returned at once."""
     basefich0 = options['basefich0']
     log = basefich0 + '_log.txt'
     if options['transversalium']:
@@ -126,7 +141,23 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
         requested, circular, cercle0, borders = _circularise_post_warp(options, disk_list, shifts, basefich0)
     else:
         requested, circular, cercle0, borders = _circularise_owned(options, disk_list, shifts, basefich0)
-    # 3. transversalium for all requested shifts (batched), then the host tail per image
+    if _defer is not None:
+        import torch
+        launched = torch.cuda.Event()
+        launched.record()                                     # the worker's kernels follow the circularisation
+
+        def finish():
+            torch.cuda.current_stream().wait_event(launched)
+            return _finish_process(options, hdr, backup_bounds, shifts, requested, circular, cercle0, borders, _pool)
+        return _defer.submit(finish)
+    return _finish_process(options, hdr, backup_bounds, shifts, requested, circular, cercle0, borders, _pool)
+
+
+def _finish_process(options, hdr, backup_bounds, shifts, requested, circular, cercle0, borders, _pool):
+    """Part 3 of solex_process: transversalium for all requested shifts (batched), then the host tail per
+    image.  No collectives: with several ranks each one works on the images it owns."""
+    basefich0 = options['basefich0']
+    log = basefich0 + '_log.txt'
     images = [circular[i] for i in requested]
     plot_jobs = []
     if options['transversalium'] and images and all(isinstance(im, DeviceImage) for im in images) \
@@ -160,7 +191,7 @@ def solex_process(options, disk_list, backup_bounds, hdr, _pool=None):
                 observer('detrans', basefich, detrans[j])
         res = single_image_process(images[j], hdr, options, cercle0, borders, basefich, backup_bounds, _pool=_pool,
                                    _detrans=None if detrans is None else detrans[j])
-        if _pool is not None:
+        if _pool is not None and hasattr(res, 'result'):      # (a result sink returns nothing to wait for)
             futures.append(res)
         write_complete(log, options)
     return futures + plot_jobs if _pool is not None else None

@@ -29,6 +29,7 @@ _PROTOS = {
     'shg_version': (i32, []),
     'shg_device_info': (i32, [i32, C.POINTER(i64)]),
     'shg_accumulate': (i32, [vp, i32, i64, i64, vp, vp, vp]),
+    'shg_frame_sums': (i32, [vp, i32, i64, i64, vp, vp]),
     'shg_finalize_mean_max': (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp]),
     'shg_box_blur_u16': (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
     'shg_row_sums_u16': (i32, [vp, i32, i32, vp, vp]),

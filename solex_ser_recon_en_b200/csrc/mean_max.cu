@@ -160,7 +160,39 @@ finalize_kernel(const unsigned long long* __restrict__ sum, const unsigned int* 
     }
 }
 
+// per-frame sum of the raw pixels (one CTA per frame): np.mean(frame) of all_video_reader.means
+template <typename T>
+__global__ void __launch_bounds__(256)
+frame_sums_kernel(const T* __restrict__ frames, int64_t frame_px, unsigned long long* __restrict__ out) {
+    const T* f = frames + (int64_t)blockIdx.x * frame_px;
+    unsigned long long s = 0;
+    for (int64_t i = threadIdx.x; i < frame_px; i += 256) s += f[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        out[blockIdx.x] = t;
+    }
+}
+
 }  // namespace
+
+extern "C" int shg_frame_sums(const void* d_frames, int bytes_per_px, int64_t n_frames, int64_t frame_px,
+                              uint64_t* d_out, void* stream) {
+    SHG_REQUIRE(bytes_per_px == 1 || bytes_per_px == 2, "shg_frame_sums: bytes_per_px must be 1 or 2");
+    if (n_frames <= 0 || frame_px <= 0) return 0;
+    SHG_REQUIRE(n_frames <= 0x7fffffff, "shg_frame_sums: too many frames");
+    auto* out = reinterpret_cast<unsigned long long*>(d_out);
+    if (bytes_per_px == 2)
+        frame_sums_kernel<uint16_t><<<(unsigned)n_frames, 256, 0, as_stream(stream)>>>((const uint16_t*)d_frames, frame_px, out);
+    else
+        frame_sums_kernel<uint8_t><<<(unsigned)n_frames, 256, 0, as_stream(stream)>>>((const uint8_t*)d_frames, frame_px, out);
+    SHG_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int shg_accumulate(const void* d_frames, int bytes_per_px, int64_t n_frames, int64_t frame_px,
                               uint64_t* d_sum, uint32_t* d_max, void* stream) {

@@ -350,6 +350,15 @@ class Engine:
         self.n_launches += 1
         stack.accumulated = True
 
+    def frame_means(self, stack: DeviceStack) -> np.ndarray:
+        """np.mean of every oriented frame of the stack (all_video_reader.means, video_reader.py:143-147)."""
+        g = stack.geom
+        sums = self.empty((stack.n,), torch.int64)
+        call('shg_frame_sums', stack.frames.data_ptr(), g.bytes_per_px, stack.n, g.frame_px, sums.data_ptr(), self.stream)
+        self.n_launches += 1
+        scale = 256 if g.bytes_per_px == 1 else 1
+        return sums.cpu().numpy().astype(np.float64) * scale / g.frame_px
+
     def finalize_mean_max(self, sum_t, max_t, n_total: int, geom: ScanGeometry):
         mean_img = self.empty((geom.ih, geom.iw), torch.uint16)
         max_img = self.empty((geom.ih, geom.iw), torch.uint16)

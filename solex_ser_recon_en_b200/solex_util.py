@@ -108,6 +108,11 @@ def resident_stack(rdr, accumulate=True) -> DeviceStack:
     or any reader with the reference's interface (all_video_reader's `frames`
     array, or frame-by-frame next_frame())."""
     eng = get_engine()
+    from .video_reader import all_video_reader
+    if isinstance(rdr, all_video_reader):                         # resident since it was opened; summed during ingest
+        if accumulate and not rdr.stack.accumulated:
+            eng.accumulate(rdr.stack, reset=True)
+        return rdr.stack
     if isinstance(rdr, device_scan):                              # already in HBM: pass 1 just re-reads it
         if accumulate:
             with eng.stage('accumulate'):
@@ -285,6 +290,9 @@ def read_video_improved(rdr, fit, options):
     # several ranks: complete disk images on their owners ('by_shift'), or -- when nothing downstream needs the
     # pixels of a complete disk on one GPU -- every rank keeps its frame rows and the (4-5 x smaller)
     # circularised images are exchanged instead ('post_warp', see parallel.py)
+    wait_previous = options.get('_before_recon')
+    if wait_previous is not None:                                  # batch mode: the previous scan's owners are done
+        wait_previous()                                            # with the buffers this scan reconstructs into
     _, size = parallel.world()
     post_warp = (size > 1 and parallel.exchange_mode() == 'post_warp' and wants_fit and not options['save_fit']
                  and not options['flag_display'] and (options['clahe_only'] or options['protus_only']))

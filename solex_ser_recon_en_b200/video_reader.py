@@ -208,38 +208,88 @@ class video_reader:
         return self.FrameIndex + 1 < self.FrameCount
 
 
+class _DeviceFrames:
+    """all_video_reader.frames for a scan that lives in HBM: indexes like the (N, ih, iw) uint16 array of the
+    reference, copying only the frames that are asked for to the host (oriented and scaled like next_frame)."""
+    dtype = np.dtype(np.uint16)
+    ndim = 3
+
+    def __init__(self, owner):
+        self._o = owner
+        self.shape = (int(owner.FrameCount), owner.ih, owner.iw)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _block(self, k0, k1):
+        o = self._o
+        blk = o.stack.host_frames(k0, k1)
+        if o.flag_rotate:
+            blk = np.rot90(blk, axes=(1, 2))
+        blk = blk.astype(np.uint16)
+        return blk * 256 if o.infiledatatype == 'uint8' else blk
+
+    def __getitem__(self, idx):
+        first = idx[0] if isinstance(idx, tuple) else idx
+        rest = idx[1:] if isinstance(idx, tuple) else ()
+        n = self.shape[0]
+        if isinstance(first, slice):
+            a, b, step = first.indices(n)
+            if step == 1:
+                blk = self._block(a, max(a, b))
+                return blk[(slice(None),) + tuple(rest)] if rest else blk
+        elif isinstance(first, (int, np.integer)):
+            k = int(first) + (n if first < 0 else 0)
+            fr = self._block(k, k + 1)[0]
+            return fr[tuple(rest)] if rest else fr
+        return np.asarray(self)[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._block(0, self.shape[0])
+        return a if dtype is None else a.astype(dtype)
+
+
 class all_video_reader:
-    """Whole scan in host RAM as oriented uint16 frames
-    (/root/reference/video_reader.py:129-158); used by interactive tools."""
+    """Whole scan resident in HBM behind the interface of the reference's in-RAM reader
+    (/root/reference/video_reader.py:129-158; used by the spectral analyser,
+    spectralAnalyserUI.py:155-175, 345-359: one compute_mean_return_fit, then read_video_improved again and
+    again at new shifts after reset()).  The file crosses PCIe ONCE here; `frames` indexes like the reference's
+    (N, ih, iw) uint16 array but copies only what is asked for to the host; `means` are the per-frame means.
+    solex_util.compute_mean_return_fit / read_video_improved recognise `.stack` and work on it in place."""
 
     def __init__(self, file, buffer_size=25):
+        from . import parallel
+        from .engine import get_engine
+        if parallel.world()[1] > 1:
+            raise Exception('all_video_reader keeps the WHOLE scan on one GPU (the interactive tools\' reader); '
+                            'under torchrun use video_reader, whose frames are sharded across the ranks')
         rdr = video_reader(file, buffer_size)
-        self.file = file
+        self.file = self.path = file
         self.ih, self.iw = rdr.ih, rdr.iw
         self.Width, self.Height = rdr.Width, rdr.Height
         self.FrameCount = rdr.FrameCount
         self.count = rdr.count
+        self.flag_rotate, self.infiledatatype = rdr.flag_rotate, rdr.infiledatatype
         self.FrameIndex = -1
-        n = int(rdr.FrameCount)
-        self.frames = np.zeros((n, self.ih, self.iw), dtype=np.uint16)
-        self.means = np.zeros(n)
-        for a in range(0, n, 64):
-            b = min(n, a + 64)
-            blk = rdr.raw_frames(a, b)
-            if rdr.flag_rotate:
-                blk = np.rot90(blk, axes=(1, 2))
-            blk = blk.astype(np.uint16)
-            if rdr.infiledatatype == 'uint8':
-                blk = blk * 256
-            self.frames[a:b] = blk
-            self.means[a:b] = blk.reshape(b - a, -1).mean(axis=1)
+        eng = get_engine()
+        g = rdr.geometry
+        if rdr.streamable:
+            self.stack, _ = eng.ingest_file(rdr.path, g, rdr.payload_offset, rdr.frame_stride, accumulate=True)
+        else:                                           # compressed AVI: host decode
+            self.stack = eng.ingest_array(np.ascontiguousarray(rdr.raw_frames(0, int(rdr.FrameCount))))
+        self.means = eng.frame_means(self.stack)
+        self.frames = _DeviceFrames(self)
+
+    @property
+    def geometry(self):
+        return self.stack.geom
 
     def has_frames(self):
         return self.FrameIndex + 1 < self.FrameCount
 
     def next_frame(self):
         self.FrameIndex += 1
-        return self.frames[self.FrameIndex, :, :]
+        return self.frames[self.FrameIndex]
 
     def reset(self):
         self.FrameIndex = -1

@@ -208,3 +208,52 @@ def test_resident_scan_is_reconstructed_again_without_reingest(tmp_path):
         eng.ingest_file = real_ingest
         solex_util.release_resident()
     assert calls == []
+
+
+@pytest.mark.parametrize('name', ['ser16_rot', 'ser8_rot_flip', 'ser16_norot'])
+def test_all_video_reader_is_device_resident_and_matches_the_reference(name, tmp_path):
+    """f3: all_video_reader (reference video_reader.py:129-158, the spectral analyser's reader) keeps the scan in
+    HBM: same attributes, `frames` slices and `means` as the reference's in-RAM reader; compute_mean_return_fit
+    and repeated reset() + read_video_improved at new shifts (spectralAnalyserUI.py:155-175, 345-346) give the
+    reference's results without the file crossing PCIe again."""
+    import time
+    from oracle import ref_shim
+    from oracle import shg_oracle as O
+    from solex_ser_recon_en_b200 import solex_util, video_reader
+    from solex_ser_recon_en_b200.engine import get_engine
+    from helpers import case_stack
+    g = golden(name)
+    _, stack = case_stack(name)
+    path = case_file(name, tmp_path)
+    eng = get_engine()
+    n_ingests = len(eng.ingest_log)
+    rdr = video_reader.all_video_reader(path)
+    assert len(eng.ingest_log) == n_ingests + 1
+    want_frames = np.stack([O.orient(f) for f in stack])
+    assert rdr.frames.shape == want_frames.shape and (rdr.ih, rdr.iw) == want_frames.shape[1:]
+    assert np.array_equal(rdr.frames[3:9, :, :], want_frames[3:9])
+    assert np.array_equal(rdr.frames[-1], want_frames[-1])
+    assert np.array_equal(np.asarray(rdr.frames), want_frames)
+    np.testing.assert_array_equal(rdr.means, want_frames.reshape(len(want_frames), -1).mean(axis=1))
+    if ref_shim.available():                                    # the reference's own reader on the same file
+        ref = ref_shim.load().video_reader.all_video_reader(path)
+        assert np.array_equal(ref.frames, want_frames) and np.array_equal(ref.means, rdr.means)
+        assert (ref.ih, ref.iw, int(ref.FrameCount)) == (rdr.ih, rdr.iw, int(rdr.FrameCount))
+    assert rdr.has_frames() and np.array_equal(rdr.next_frame(), want_frames[0]) and rdr.FrameIndex == 0
+    opt = options_for(name, tmp_path, _nolog=True)
+    mean_img, fit, y1, y2 = solex_util.compute_mean_return_fit(rdr, opt, {}, rdr.iw, rdr.ih, '')
+    assert np.array_equal(mean_img, g['mean_img']) and (y1, y2) == (int(g['y1']), int(g['y2']))
+    lat = []
+    for shifts in ([10], [0], [-7, 3, 12], [1]):
+        opt['shift'] = shifts
+        rdr.reset()
+        eng.sync()
+        t0 = time.perf_counter()
+        disks, ih, iw, n = solex_util.read_video_improved(rdr, fit, opt)
+        eng.sync()
+        lat.append((time.perf_counter() - t0) * 1e3 / len(shifts))
+        ref_disks = O.recon(stack, fit, shifts)
+        for i in range(len(shifts)):
+            assert np.array_equal(np.asarray(disks[i]), ref_disks[i]), shifts[i]
+    assert len(eng.ingest_log) == n_ingests + 1                 # the scan crossed PCIe once
+    assert min(lat) < 5.0, lat                                  # ms per shift on these tiny scans (launch-bound)
