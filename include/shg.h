@@ -170,6 +170,29 @@ int shg_warp_rows_window(const uint16_t* d_disk, int64_t disk_stride, const int3
                          int out_cols, const uint32_t* d_cval, int own_lo, int own_hi,
                          const uint64_t* d_out_ptrs, void* stream);
 
+/* The TMA formulation of the same warp (csrc/warp.cu, warp_tma_kernel): the input tile is staged by
+ * cp.async.bulk.tensor boxes, a lane owns a slit row and walks output columns, eight pixels leave as one 16-byte
+ * store.  Identical results.  The disks are described as they lie in memory: d_disk points at frame
+ * `frame_origin` (PHYSICAL frame index) of image 0, n_local_frames frames per image are present, images are
+ * disk_stride elements apart and there are n_disk_images of them (d_sel picks among them).  Complete images:
+ * frame_origin 0, n_local_frames == n_frames, own_lo / own_hi = INT_MIN / INT_MAX.  Frame-sharded scans: the
+ * rank's frames plus its halo, [own_lo, own_hi) in logical order as for shg_warp_rows_window, d_cval required.
+ * Needs ih % 8 == 0, disk_stride % 8 == 0 and 16-byte aligned buffers: shg_warp_rows_tma_ok() says whether a
+ * geometry qualifies (else use shg_warp_rows / shg_warp_rows_window). */
+int shg_warp_rows_tma_ok(const uint16_t* d_disk, int64_t disk_stride, int ih, const uint16_t* d_out, int64_t out_stride,
+                         const uint64_t* d_out_ptrs);
+int shg_warp_rows_tma(const uint16_t* d_disk, int64_t disk_stride, int n_disk_images, int64_t n_local_frames,
+                      int64_t frame_origin, const int32_t* d_sel, int n_imgs, int64_t n_frames, int ih, int flip,
+                      double m00, double m01, double m02, const uint32_t* d_minmax, uint16_t* d_out, int64_t out_stride,
+                      int out_rows, int out_cols, const uint32_t* d_cval, int own_lo, int own_hi,
+                      const uint64_t* d_out_ptrs, void* stream);
+/* Exchange step of the frame-sharded circularisation: copy, for every image and row, the columns this
+ * rank produced (left tap in [own_lo, own_hi): one interval per row) from its local full-width images
+ * (d_local + i*local_stride) into the image's owner (d_out_ptrs[i], local or PEER memory) with 16-byte stores in
+ * 512-byte contiguous runs per warp.  Rows whose destination is the source are skipped. */
+int shg_exchange_rows(const uint16_t* d_local, int64_t local_stride, int n_imgs, int out_rows, int out_cols, double m00,
+                      double m01, double m02, int own_lo, int own_hi, const uint64_t* d_out_ptrs, void* stream);
+
 /* ---- a11 helper: 4x4 block sums (reference ellipse_to_circle.py:301) ---- */
 /* downscale_local_mean numerator: out[ri][ci] = sum of the 4x4 block of the
  * (ih, n_frames) image (zero padded), from a frame-major disk. */

@@ -50,6 +50,10 @@ _PROTOS = {
     'shg_warp_rows': (i32, [vp, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp]),
     'shg_warp_rows_window': (i32, [vp, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp, i32, i32,
                                    vp, vp]),
+    'shg_warp_rows_tma_ok': (i32, [vp, i64, i32, vp, i64, vp]),
+    'shg_warp_rows_tma': (i32, [vp, i64, i32, i64, i64, vp, i32, i64, i32, i32, dbl, dbl, dbl, vp, vp, i64, i32, i32, vp,
+                                i32, i32, vp, vp]),
+    'shg_exchange_rows': (i32, [vp, i64, i32, i32, i32, dbl, dbl, dbl, i32, i32, vp, vp]),
     'shg_downscale4_sum': (i32, [vp, i64, i32, i32, vp, i32, i32, vp]),
     'shg_box_sum_u32': (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
     'shg_sum_u32': (i32, [vp, i64, vp, vp]),

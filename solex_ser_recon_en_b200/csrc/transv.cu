@@ -980,21 +980,25 @@ row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int 
         p = p > 0.0 ? p : 0.0;
         return double_floor_to_u32(p) & 0xffffu;
     };
-    const bool vec = (cols % 8 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    if (vec) {
-        const int nv = cols / 8;
-        for (int v = blockIdx.x * 256 + threadIdx.x; v < nv; v += gridDim.x * 256) {
-            const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(src) + v);
-            uint4 o;
-            o.x = one(q.x & 0xffffu) | (one(q.x >> 16) << 16);
-            o.y = one(q.y & 0xffffu) | (one(q.y >> 16) << 16);
-            o.z = one(q.z & 0xffffu) | (one(q.z >> 16) << 16);
-            o.w = one(q.w & 0xffffu) | (one(q.w >> 16) << 16);
-            reinterpret_cast<uint4*>(dst)[v] = o;
-        }
-    } else {
-        for (int c = blockIdx.x * 256 + threadIdx.x; c < cols; c += gridDim.x * 256) dst[c] = (uint16_t)one(src[c]);
+    // 16-byte body on this row's own 16-byte grid (rows of an odd width start misaligned): head and tail by pixel
+    const int mis = (int)(((uintptr_t)src & 15) >> 1);                         // pixels past a 16-byte boundary
+    const bool same = (((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0 && (((uintptr_t)src & 1) == 0);
+    const int head = same ? min(cols, (8 - mis) & 7) : cols;
+    const int nv = same ? (cols - head) / 8 : 0;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < head; c += gridDim.x * 256) dst[c] = (uint16_t)one(src[c]);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < nv; v += gridDim.x * 256) {
+        const uint4 q = ld_stream_u4(s4 + v);
+        uint4 o;
+        o.x = one(q.x & 0xffffu) | (one(q.x >> 16) << 16);
+        o.y = one(q.y & 0xffffu) | (one(q.y >> 16) << 16);
+        o.z = one(q.z & 0xffffu) | (one(q.z >> 16) << 16);
+        o.w = one(q.w & 0xffffu) | (one(q.w >> 16) << 16);
+        d4[v] = o;
     }
+    for (int c = head + nv * 8 + blockIdx.x * 256 + threadIdx.x; c < cols; c += gridDim.x * 256)
+        dst[c] = (uint16_t)one(src[c]);
 }
 
 }  // namespace

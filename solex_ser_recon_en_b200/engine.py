@@ -540,18 +540,39 @@ class Engine:
             minmax_dev = self.minmax_device(disks, sel)
         oh, ow = int(out_shape[0]), int(out_shape[1])
         sharded = n_frames is not None
+        m00, m01, m02 = float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2])
         if not sharded:
             if out is None:
                 out = self.empty((n_imgs, oh, ow), torch.uint16)
-            call('shg_warp_rows', disks.data_ptr(), disks.stride(0), _ptr(sel_t), n_imgs, n, ih, 1 if flip else 0,
-                 float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), out.data_ptr(),
-                 out.stride(0), oh, ow, self.stream)
+            if lib.shg_warp_rows_tma_ok(disks.data_ptr(), disks.stride(0), ih, out.data_ptr(), out.stride(0), None):
+                call('shg_warp_rows_tma', disks.data_ptr(), disks.stride(0), disks.shape[0], n, 0, _ptr(sel_t), n_imgs,
+                     n, ih, 1 if flip else 0, m00, m01, m02, minmax_dev.data_ptr(), out.data_ptr(), out.stride(0),
+                     oh, ow, None, -2 ** 31, 2 ** 31 - 1, None, self.stream)
+            else:                          # odd geometries (ih not a multiple of 8, unaligned views): direct-load kernel
+                call('shg_warp_rows', disks.data_ptr(), disks.stride(0), _ptr(sel_t), n_imgs, n, ih, 1 if flip else 0,
+                     m00, m01, m02, minmax_dev.data_ptr(), out.data_ptr(), out.stride(0), oh, ow, self.stream)
             self.n_launches += 1
             return out
         assert cvals is not None and window is not None and (out is not None or out_ptrs is not None)
+        if lib.shg_warp_rows_tma_ok(disks.data_ptr(), disks.stride(0), ih, _ptr(out), 0 if out is None else out.stride(0),
+                                    None) and (out is not None or (oh * ow) % 8 == 0):
+            # this rank's pixels into a local full-width image (16-byte stores), then one copy kernel moves every
+            # row interval into the image's owner in 512-byte runs (peer stores of 16 or 64 bytes crawl over NVLink)
+            local = out if out is not None else self.empty((n_imgs, oh, ow), torch.uint16)
+            call('shg_warp_rows_tma', disks.data_ptr(), disks.stride(0), disks.shape[0], disks.shape[1],
+                 int(frame_origin), _ptr(sel_t), n_imgs, int(n_frames), ih, 1 if flip else 0, m00, m01, m02,
+                 minmax_dev.data_ptr(), local.data_ptr(), local.stride(0), oh, ow, cvals.data_ptr(), int(window[0]),
+                 int(window[1]), None, self.stream)
+            self.n_launches += 1
+            if out_ptrs is not None:
+                call('shg_exchange_rows', local.data_ptr(), local.stride(0), n_imgs, oh, ow, m00, m01, m02,
+                     int(window[0]), int(window[1]), out_ptrs.data_ptr(), self.stream)
+                self.n_launches += 1
+                local.record_stream(torch.cuda.current_stream(self.device))
+            return out
         base = disks.data_ptr() - int(frame_origin) * ih * 2          # frame 0 of the whole scan (never dereferenced there)
         call('shg_warp_rows_window', base, disks.stride(0), _ptr(sel_t), n_imgs, int(n_frames), ih, 1 if flip else 0,
-             float(mat3[0, 0]), float(mat3[0, 1]), float(mat3[0, 2]), minmax_dev.data_ptr(), _ptr(out),
+             m00, m01, m02, minmax_dev.data_ptr(), _ptr(out),
              0 if out is None else out.stride(0), oh, ow, cvals.data_ptr(), int(window[0]), int(window[1]),
              _ptr(out_ptrs), self.stream)
         self.n_launches += 1

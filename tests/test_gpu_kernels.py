@@ -627,3 +627,102 @@ def test_gain_kernel_matches_reference_arithmetic(eng, n, strength):
     for i in range(stats.shape[0]):
         want = O.transversalium_gain(np.concatenate([[0.0], stats[i]]), y1, y1 + n, n_rows, strength)
         np.testing.assert_allclose(g[i], want, rtol=1e-9)
+
+
+# ------------------------------------------------ warp: TMA formulation (a10)
+@pytest.mark.parametrize('rows,n,phi,ratio,flip', [
+    (192, 333, 0.0, 1.0, False), (200, 1000, 0.12, 0.83, False), (136, 777, -0.2, 1.31, True),
+    (64, 5000, 0.001, 0.195, False),             # the config-5 stretch: 5 frames per output column, 64-column tiles
+    (328, 2100, -0.0004, 0.25, True), (72, 90, 0.6, 3.1, False), (1032, 400, 0.0, 2.4, False)])
+def test_warp_tma_matches_oracle(eng, rows, n, phi, ratio, flip):
+    """The TMA kernel (ih a multiple of 8: staged by cp.async.bulk.tensor, one lane per slit row, 16-byte stores on
+    each row's own 16-byte grid) against the oracle and against the direct-load kernel, for tile-edge cases: rows
+    not a multiple of 64, odd / even output widths, shear of either sign, flips, strong stretch and squeeze."""
+    import torch
+    from solex_ser_recon_en_b200 import geometry
+    from solex_ser_recon_en_b200._lib import call, lib
+    rng = np.random.default_rng(rows + n)
+    img = rng.integers(256, 60000, size=(rows, n)).astype(np.uint16)
+    img[rows // 3:rows // 2, n // 4:n // 2] = img.min()
+    logical = np.ascontiguousarray(img[:, ::-1]) if flip else img
+    want, _ = O.warp_rows(logical, phi, ratio)
+    _, mat3, (oh, ow), _, _ = geometry.warp_plan((rows, n), phi, ratio)
+    fm = torch.from_numpy(np.ascontiguousarray(img.T).view(np.int16)).to(eng.device).view(torch.uint16)   # (n, rows)
+    mm = eng.minmax_device(fm)
+    assert lib.shg_warp_rows_tma_ok(fm.data_ptr(), fm.numel(), rows, fm.data_ptr(), oh * ow + (-(oh * ow)) % 8, None)
+    got = eng.warp_batch(fm, None, flip, mat3, (oh, ow), mm)
+    assert np.array_equal(u16(got[0]), want)
+    old = eng.empty((1, oh, ow), torch.uint16)
+    call('shg_warp_rows', fm.data_ptr(), fm.numel(), 0, 1, n, rows, 1 if flip else 0, float(mat3[0, 0]), float(mat3[0, 1]),
+         float(mat3[0, 2]), mm.data_ptr(), old.data_ptr(), oh * ow, oh, ow, eng.stream)
+    assert torch.equal(old.view(torch.int16), got.view(torch.int16))
+
+
+def test_warp_tma_batch_with_selection(eng):
+    """Several images of one disk tensor in one launch (d_sel), each with its own clip range and [0][0] pixel."""
+    import torch
+    from solex_ser_recon_en_b200 import geometry
+    rng = np.random.default_rng(3)
+    rows, n, S = 128, 640, 5
+    imgs = rng.integers(100, 50000, size=(S, rows, n)).astype(np.uint16)
+    disk = torch.from_numpy(np.ascontiguousarray(imgs.transpose(0, 2, 1)).view(np.int16)).to(eng.device).view(torch.uint16)
+    _, mat3, (oh, ow), _, _ = geometry.warp_plan((rows, n), 0.05, 0.4)
+    sel = [4, 1, 2]
+    mm = eng.minmax_device(disk, sel)
+    got = eng.warp_batch(disk, sel, False, mat3, (oh, ow), mm)
+    for j, s_ in enumerate(sel):
+        want, _ = O.warp_rows(imgs[s_], 0.05, 0.4)
+        assert np.array_equal(u16(got[j]), want), s_
+
+
+@pytest.mark.parametrize('size,flip,phi,ratio', [(2, False, 0.0, 0.3), (3, True, 0.05, 0.25), (4, False, -0.2, 1.7),
+                                                 (8, True, 0.0004, 0.21)])
+def test_warp_sharded_tma_and_exchange_tile_the_image(eng, size, flip, phi, ratio):
+    """The frame-sharded circularisation, all ranks simulated on one GPU: every rank warps its own frames (+ halo)
+    into a local full-width image with the TMA kernel and shg_exchange_rows copies its row intervals into the
+    owner's image.  The union must be the single-pass image bit for bit, for every world size / flip / tilt."""
+    import torch
+    from solex_ser_recon_en_b200 import geometry, parallel
+    rng = np.random.default_rng(size)
+    rows, n, S = 136, 997, 3
+    imgs = rng.integers(100, 50000, size=(S, rows, n)).astype(np.uint16)          # physical frame order
+    _, mat3, (oh, ow), _, _ = geometry.warp_plan((rows, n), phi, ratio)
+    full = torch.from_numpy(np.ascontiguousarray(imgs.transpose(0, 2, 1)).view(np.int16)).to(eng.device).view(torch.uint16)
+    mm = eng.minmax_device(full)
+    want = eng.warp_batch(full, None, flip, mat3, (oh, ow), mm)
+    for j in range(S):
+        logical = np.ascontiguousarray(imgs[j][:, ::-1]) if flip else imgs[j]
+        assert np.array_equal(u16(want[j]), O.warp_rows(logical, phi, ratio)[0])
+    pad = (-(oh * ow)) % 8
+    owner_buf = torch.zeros((S * (oh * ow + pad),), dtype=torch.int16, device=eng.device).view(torch.uint16)
+    ptrs = eng.upload(np.asarray([owner_buf.data_ptr() + j * (oh * ow + pad) * 2 for j in range(S)], dtype=np.int64))
+    cvals = eng.upload(np.asarray([int(imgs[j][0, n - 1 if flip else 0]) for j in range(S)], dtype=np.int32))
+    h = parallel.halo_frames(n, size)
+    for rank in range(size):
+        k0, k1 = parallel.frame_range(n, rank, size)
+        a, b = max(0, k0 - h), min(n, k1 + h)
+        local = full.view(torch.int16)[:, a:b].contiguous().view(torch.uint16)   # this rank's frames and its halo
+        lo, hi = parallel.owned_logical_frames(n, rank, size, flip)
+        eng.warp_batch(local, None, flip, mat3, (oh, ow), mm, n_frames=n, frame_origin=a, cvals=cvals,
+                       window=(lo, hi), out_ptrs=ptrs)
+    eng.sync()
+    got = owner_buf.view(torch.int16).cpu().numpy().view(np.uint16).reshape(S, oh * ow + pad)[:, :oh * ow].reshape(S, oh, ow)
+    for j in range(S):
+        assert np.array_equal(got[j], u16(want[j])), (size, j)
+
+
+def test_warp_tma_tiles_beside_the_image(eng):
+    """Strong shear: whole tiles lie left / right of the image (every tap is the fill constant) -- nothing is staged
+    for them, and frame-sharded ranks at the ends of the scan still own those pixels."""
+    import torch
+    from solex_ser_recon_en_b200 import geometry
+    rng = np.random.default_rng(12)
+    rows, n = 1024, 600
+    img = rng.integers(300, 40000, size=(rows, n)).astype(np.uint16)
+    for phi, ratio in ((0.02, 0.195), (-0.3, 0.4)):
+        want, _ = O.warp_rows(img, phi, ratio)
+        _, mat3, (oh, ow), _, _ = geometry.warp_plan((rows, n), phi, ratio)
+        fm = torch.from_numpy(np.ascontiguousarray(img.T).view(np.int16)).to(eng.device).view(torch.uint16)
+        mm = eng.minmax_device(fm)
+        got = eng.warp_batch(fm, None, False, mat3, (oh, ow), mm)
+        assert np.array_equal(u16(got[0]), want), (phi, ratio)

@@ -130,6 +130,28 @@ def main():
         ms, best = timed(lambda: eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ), a.reps)
         res['warp'] = dict(ms=ms, best_ms=best, GBps=(img_bytes + oh * ow * 2) / ms / 1e6, out=(oh, ow))
     eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ)
+    if want('batch'):
+        # the launches of the real step: every image of the scan in one call (what profiles/ must show)
+        n_img = len(shifts)
+        mm_all = eng.minmax_device(disk)
+        circ_all = eng.empty((n_img, oh, ow), torch.uint16)
+        ms, best = timed(lambda: eng.warp_batch(disk, None, False, mat3, (oh, ow), mm_all, out=circ_all), a.reps)
+        res['warp_batch'] = dict(ms=ms, best_ms=best, GBps=n_img * (img_bytes + oh * ow * 2) / ms / 1e6, images=n_img,
+                                 out=(oh, ow))
+        os.environ['SHG_WARP_OLD'] = '1'
+        ms, best = timed(lambda: eng.warp_batch(disk, None, False, mat3, (oh, ow), mm_all, out=circ_all), a.reps)
+        res['warp_batch_direct_load_kernel'] = dict(ms=ms, best_ms=best, GBps=n_img * (img_bytes + oh * ow * 2) / ms / 1e6)
+        del os.environ['SHG_WARP_OLD']
+        cy_, cx_, rad_ = oh / 2.0, ow / 2.0, 0.40 * geom.ih
+        y1_, y2_, rows_, xa_, xb_ = eng.transversalium_chords((cx_, cy_, rad_), [0, 0, ow - 1, oh - 1])
+        ms, best = timed(lambda: eng.transversalium_row_stats(circ_all, rows_, xa_, xb_, device=True), a.reps)
+        res['transv_stats_batch'] = dict(ms=ms, best_ms=best, GBps=n_img * 2.0 * float((xb_ - xa_).sum()) * 2 / ms / 1e6,
+                                         rows=len(rows_), images=n_img)
+        gains_all = torch.ones((n_img, oh), dtype=torch.float64, device=eng.device)
+        det_all = eng.empty((n_img, oh, ow), torch.uint16)
+        ms, best = timed(lambda: eng.row_scale(circ_all, gains_all, out=det_all), a.reps)
+        res['row_scale_batch'] = dict(ms=ms, best_ms=best, GBps=n_img * 2 * oh * ow * 2 / ms / 1e6)
+        del circ_all, det_all
     cy, cx, rad = oh / 2.0, ow / 2.0, 0.40 * geom.ih
     y1, y2, rows, xa, xb = eng.transversalium_chords((cx, cy, rad), [0, 0, ow - 1, oh - 1])
     if want('transv'):
