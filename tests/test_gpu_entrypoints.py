@@ -257,3 +257,39 @@ def test_all_video_reader_is_device_resident_and_matches_the_reference(name, tmp
             assert np.array_equal(np.asarray(disks[i]), ref_disks[i]), shifts[i]
     assert len(eng.ingest_log) == n_ingests + 1                 # the scan crossed PCIe once
     assert min(lat) < 5.0, lat                                  # ms per shift on these tiny scans (launch-bound)
+
+
+@pytest.mark.parametrize('shape', [(200, 300), (201, 303), (416, 531), (1024, 1221)])
+def test_device_tail_equals_opencv_clahe_and_numpy_rescales(shape, tmp_path):
+    """f2: image_process on a DeviceImage (CLAHE + percentile rescales on the GPU, csrc/tail.cu) against the host
+    path that calls cv2.createCLAHE / np.percentile like the reference (solex_util.py:527-546): identical images,
+    for even and odd sizes (OpenCV extends odd images by reflection before cutting tiles)."""
+    import cv2
+    import torch
+    from solex_ser_recon_en_b200 import solex_util
+    from solex_ser_recon_en_b200.device_image import DeviceImage
+    from solex_ser_recon_en_b200.engine import get_engine
+    eng = get_engine()
+    rng = np.random.default_rng(shape[0])
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    rho2 = ((yy - shape[0] / 2) / (0.4 * shape[0])) ** 2 + ((xx - shape[1] / 2) / (0.42 * shape[1])) ** 2
+    img = np.where(rho2 < 1, 30000 * np.sqrt(np.clip(1 - 0.6 * rho2, 0, 1)), 600.0) + rng.normal(0, 50, shape) + 300
+    img = np.clip(img, 0, 65535).astype(np.uint16)
+    img[5, 7] = 65535                                         # a hot pixel: the 99.9999 percentile interpolates to it
+    opt = options_for('ser16_rot', tmp_path, clahe_only=False)
+    opt.pop('_nolog', None)
+    cercle = (shape[1] / 2.0, shape[0] / 2.0, 0.4 * shape[0])
+    out_h, out_d = os.path.join(str(tmp_path), 'host'), os.path.join(str(tmp_path), 'dev')
+    os.makedirs(out_h), os.makedirs(out_d)
+    cc_h, pr_h = solex_util.image_process(img, cercle, dict(opt, output_dir=out_h), {}, 'tail_shift=0')
+    t = torch.from_numpy(img.view(np.int16)).to(eng.device).view(torch.uint16)
+    cc_d, pr_d = solex_util.image_process(DeviceImage(eng, t), cercle, dict(opt, output_dir=out_d), {}, 'tail_shift=0')
+    assert np.array_equal(cc_d, cc_h) and np.array_equal(pr_d, pr_h)
+    assert np.array_equal(cc_h, solex_util.rescale_brightness(
+        cv2.createCLAHE(clipLimit=0.8, tileGridSize=(2, 2)).apply(img), np.percentile(
+            cv2.createCLAHE(clipLimit=0.8, tileGridSize=(2, 2)).apply(img), 10),
+        np.max(cv2.createCLAHE(clipLimit=0.8, tileGridSize=(2, 2)).apply(img))))
+    for name in ('clahe', 'protus', 'uncontrasted', 'high_contrast'):
+        a = cv2.imread(os.path.join(out_h, 'tail_shift=0_%s.png' % name), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(os.path.join(out_d, 'tail_shift=0_%s.png' % name), cv2.IMREAD_UNCHANGED)
+        assert a is not None and b is not None and np.array_equal(a, b), name
