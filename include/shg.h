@@ -102,8 +102,9 @@ int shg_fit_table(const double* d_coef, int ih, double* d_fit /* ih x 4 */, void
  * from shg_ipc_open), so each rank writes its frame rows straight into the
  * owner's image over NVLink -- reconstruction and the row exchange are one
  * kernel.  d_work: device scratch of at least shg_recon_workspace_bytes(ih,
- * n_shifts) bytes.  impl: 0 = auto, 1 = generic direct-load kernel, 2 = TMA
- * band kernel.
+ * n_shifts) bytes.  impl: bits 0-7: 0 = auto, 1 = generic direct-load kernel, 2 = TMA
+ * band kernel; bits 8-15: use at most that many SMs (0 = all), for callers that run
+ * latency-critical small kernels beside this one.
  * d_min (optional, device uint32[n_shifts], in the order of h_shifts): the kernel
  * folds min(d_min[s], minimum of the pixels it writes for shift s) into it, so the
  * caller pre-fills it with 65535 (or the partial minimum of other frame ranges);

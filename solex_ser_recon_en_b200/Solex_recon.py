@@ -256,6 +256,9 @@ def _circularise_post_warp(options, disk_list, shifts, basefich0):
     """The same for frame-sharded images (exchange mode 'post_warp'): the list of requested shifts is the
     same on every rank; the circularised images land on their owners (by position in that list)."""
     req_all = [i for i in range(len(disk_list)) if shifts[i] in options['shift_requested']]
+    # everything of the circularisation that does not depend on the geometry (index lists, clip ranges, fill
+    # constants: a few small uploads and index kernels) is prepared BEFORE waiting for the fit / the broadcast
+    prepared = postprocess.prepare_partial([disk_list[i] for i in req_all])
     geom, failure = None, None
     full0 = disk_list[0].full
     if full0 is not None:                                     # rank 0: the gathered ellipse-fit image
@@ -269,7 +272,7 @@ def _circularise_post_warp(options, disk_list, shifts, basefich0):
         cercle0, options['ratio_fixe'], phi, borders = parallel.broadcast_geometry(geom, 0, failure)
     options['slant_fix'] = math.degrees(phi)
     phi = math.radians(options['slant_fix'])                  # the same degrees round trip as the single-GPU path
-    warped = postprocess.circularise_partial([disk_list[i] for i in req_all], phi, options['ratio_fixe'])
+    warped = postprocess.circularise_partial([disk_list[i] for i in req_all], phi, options['ratio_fixe'], prepared)
     requested = [i for q, i in enumerate(req_all) if warped[q] is not None]
     circular = {i: warped[q] for q, i in enumerate(req_all) if warped[q] is not None}
     return requested, circular, cercle0, borders

@@ -463,7 +463,12 @@ extern "C" int64_t shg_recon_workspace_bytes(int ih, int n_shifts) {
 extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frames, int W, int H,
                          const double* h_fit, const int32_t* h_shifts, int n_shifts,
                          uint16_t* d_disk, int64_t shift_stride, const uint64_t* h_out_ptrs, int64_t k0_out,
-                         int impl, void* d_work, int64_t work_bytes, uint32_t* d_min, int* h_min_done, void* stream) {
+                         int impl_and_cap, void* d_work, int64_t work_bytes, uint32_t* d_min, int* h_min_done, void* stream) {
+    // bits 0-7: kernel variant (0 auto, 1 direct loads, 2 TMA); bits 8-15: use at most that many SMs (0 = all).  A
+    // caller that runs latency-critical small kernels beside this one (the limb search of the ellipse fit while the
+    // other shifts are reconstructed, on several GPUs) leaves them a few SMs: the persistent CTAs of this kernel
+    // otherwise hold every SM until it ends.
+    const int impl = impl_and_cap & 0xff, sm_cap = (impl_and_cap >> 8) & 0xff;
     if (h_min_done) *h_min_done = 0;
     SHG_REQUIRE(bytes_per_px == 1 || bytes_per_px == 2, "shg_recon: bytes_per_px must be 1 or 2");
     SHG_REQUIRE(n_shifts >= 1 && n_shifts <= kMaxShifts, "shg_recon: %d shifts (max %d)", n_shifts, kMaxShifts);
@@ -602,6 +607,7 @@ extern "C" int shg_recon(const void* d_frames, int bytes_per_px, int64_t n_frame
     int dev = 0, sms = SHG_SM_COUNT_B200;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sm_cap > 0) sms = std::max(plan.n_tx, std::min(sms, sm_cap));
     size_t smem = (size_t)plan.stage_elems * bytes_per_px * stages + 128;
     int pair = (W % 2 == 0) ? 1 : 0;                     // column-pair kernel (default); SHG_RECON_PAIR=0 selects the other
     if (const char* e = getenv("SHG_RECON_PAIR")) pair = pair && atoi(e) != 0;

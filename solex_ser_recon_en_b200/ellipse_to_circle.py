@@ -39,12 +39,14 @@ def _as_frames(eng, image):
 
 def _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height):
     """The block correct_image prints / logs when print_log is set (reference :123-144)."""
+    print('unrotation angle theta = ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
+    print('Y/X ratio : ' + '{:.3f}'.format(ratio))
+    if '_nolog' in options:                                   # logme would drop every line: do not format them
+        return
     basefich0 = options['basefich0']
     log = basefich0 + '_log.txt'
-    print('unrotation angle theta = ' + '{:.3f}'.format(math.degrees(theta)) + ' degrees')
     np.set_printoptions(suppress=True)
     logme(log, options, 'Y/X ratio : ' + '{:.3f}'.format(ratio))
-    print('Y/X ratio : ' + '{:.3f}'.format(ratio))
     logme(log, options, 'Tilt angle : ' + '{:.3f}'.format(math.degrees(phi)) + ' degrees')
     logme(log, options, 'Linear transform correction matrix : \n' + str(mat))
     where = (str(new_center) + ', ' + '{:.3f}'.format(new_radius)) if not height == -1.0 else 'UNKNOWN'
@@ -105,8 +107,23 @@ def start_fit(image, ready=None):
     def job():
         torch.cuda.set_device(eng.device)
         with torch.cuda.stream(side):
-            return _fit_points(eng, frames, flip)
+            pts = _fit_points(eng, frames, flip)
+        n, ih = frames.shape
+        return pts, _derived_geometry(pts, (ih, n))      # the caller only has to log it
     return _fit_pool.submit(job)
+
+
+def _derived_geometry(fit_points, shape):
+    """What correct_image / ellipse_to_circle derive from the fitted ellipse (reference :100-122, 310-314): the
+    correction matrix, the disk's centre and radius after the warp, and the bounding box of the limb points."""
+    center, height, phi, ratio, kept, raw, outline = fit_points
+    mat, mat3, _, _, theta = geometry.warp_plan(shape, phi, ratio)
+    new_center, new_radius = geometry.moved_circle(center, height, phi, ratio, shape)
+    pts = np.ones((kept.shape[0], 3))
+    pts[:, 0], pts[:, 1] = kept[:, 1], kept[:, 0]                             # (row, col) -> (x, y)
+    moved = (np.linalg.inv(mat3) @ pts.T).T
+    borders = [np.min(moved[:, 0]), np.min(moved[:, 1]), np.max(moved[:, 0]), np.max(moved[:, 1])]
+    return dict(mat=mat, mat3=mat3, theta=theta, new_center=new_center, new_radius=new_radius, borders=borders)
 
 
 def fit_geometry(image, options, basefich=None):
@@ -120,19 +137,17 @@ def fit_geometry(image, options, basefich=None):
     early = getattr(image, 'fit_future', None)
     if early is not None:
         image.fit_future = None
-        center, height, phi, ratio, kept, raw, outline = early.result()      # started under the reconstruction
+        fit_points, d = early.result()                                       # started under the reconstruction
     else:
-        center, height, phi, ratio, kept, raw, outline = _fit_points(eng, frames, flip)
-    mat, mat3, _, _, theta = geometry.warp_plan((ih, n), phi, ratio)
-    new_center, new_radius = geometry.moved_circle(center, height, phi, ratio, (ih, n))
-    _log_geometry(options, mat, theta, phi, ratio, new_center, new_radius, height)
-    pts = np.ones((kept.shape[0], 3))
-    pts[:, 0], pts[:, 1] = kept[:, 1], kept[:, 0]                             # (row, col) -> (x, y)
-    moved = (np.linalg.inv(mat3) @ pts.T).T
-    borders = [np.min(moved[:, 0]), np.min(moved[:, 1]), np.max(moved[:, 0]), np.max(moved[:, 1])]
+        fit_points = _fit_points(eng, frames, flip)
+        d = _derived_geometry(fit_points, (ih, n))
+    center, height, phi, ratio, kept, raw, outline = fit_points
+    _log_geometry(options, d['mat'], d['theta'], phi, ratio, d['new_center'], d['new_radius'], height)
+    borders = d['borders']
     print('sun borders found:' + str(borders))
-    return dict(phi=phi, ratio=ratio, circle=(new_center[0], new_center[1], new_radius), borders=borders, mat3=mat3,
-                center=center, height=height, kept=kept, raw=raw, outline=outline, frames=frames, flip=flip)
+    return dict(phi=phi, ratio=ratio, circle=(d['new_center'][0], d['new_center'][1], d['new_radius']), borders=borders,
+                mat3=d['mat3'], center=center, height=height, kept=kept, raw=raw, outline=outline, frames=frames,
+                flip=flip)
 
 
 def ellipse_to_circle(image, options, basefich):

@@ -412,7 +412,8 @@ class Engine:
         if n < 4:
             raise ShgError('spectral line fit needs at least 4 slit rows, got %d (y1=%d, y2=%d)' % (n, y1, y2))
         mi, ms = det['min_intensity'][y1:y2], det['min_sharp'][y1:y2]
-        coef = self.empty((3, 4), torch.float64)
+        packed = self.empty((12 + 4 * ih,), torch.float64)          # coefficients and fit table: one download
+        coef = packed[:12].view(3, 4)
         resid = self.empty((n,), torch.float64)
         keep = self.empty((n,), torch.uint8)
         good = self.empty((n,), torch.uint8)
@@ -428,11 +429,12 @@ class Engine:
         shift = float(values[ind[0]])
         call('shg_window_mask', resid.data_ptr(), n, shift, 5.0, good.data_ptr(), st)
         call('shg_polyfit3', ms.data_ptr(), good.data_ptr(), y1, n, coef[2].data_ptr(), 0, 0, st)
-        fit = self.empty((ih, 4), torch.float64)
+        fit = packed[12:].view(ih, 4)
         call('shg_fit_table', coef[2].data_ptr(), ih, fit.data_ptr(), st)
         self.n_launches += 3
-        coef_h = coef.cpu().numpy()
-        return dict(p1=coef_h[0], p2=coef_h[1], p3=coef_h[2], shift=shift, fit=fit.cpu().numpy(),
+        packed_h = packed.cpu().numpy()
+        coef_h = packed_h[:12].reshape(3, 4)
+        return dict(p1=coef_h[0], p2=coef_h[1], p3=coef_h[2], shift=shift, fit=packed_h[12:].reshape(ih, 4),
                     keep=keep, mask_good=good)
 
     # ------------------------------------------------------- pass 2: recon
@@ -534,7 +536,10 @@ class Engine:
                 mat3[2, 0] == 0 and mat3[2, 1] == 0 and mat3[2, 2] == 1):
             raise ShgError('warp matrix is not the row-preserving form get_correction_matrix produces')
         n_imgs = disks.shape[0] if sel is None else len(sel)
-        sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
+        if isinstance(sel, torch.Tensor):                   # already on the device (prepared ahead of time)
+            sel_t = sel
+        else:
+            sel_t = None if sel is None else self.upload(np.asarray(list(sel), dtype=np.int32))
         if minmax_dev is None:
             assert n_frames is None, 'a frame-sharded warp needs the clip range of the whole images'
             minmax_dev = self.minmax_device(disks, sel)

@@ -276,7 +276,7 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
         device_barrier()                   # every rank's rows of image 0 have landed on rank 0
         ready = torch.cuda.Event()
         ready.record()
-        eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0, mins=mins[1:])
+        eng.recon(stack, fit, shifts[1:], out_ptrs=ex.ptrs[1:], k0_out=stack.k0, mins=mins[1:], impl=_beside_fit())
         known[1:] = [eng.recon_min_done] * (n_s - 1)
         if ex.owner[0] == rank:
             first_done(ex.images[0], ready)            # image 0 is complete once `ready` has passed
@@ -290,6 +290,15 @@ def reconstruct(stack, fit: np.ndarray, shifts, first_done=None):
     for n, j in enumerate(ex.mine):
         out[j] = ex.images[n]
     return out, mins, known
+
+
+def _beside_fit() -> int:
+    """shg_recon's impl word for the big reconstruction on several GPUs: the limb search of the ellipse fit runs
+    beside it on rank 0 and IS the critical path there (every rank waits for the geometry), so the persistent
+    reconstruction kernel leaves it a quarter of the SMs (SHG_RECON_SM_CAP overrides; 0 = no cap).  The same cap
+    on every rank keeps the kernel variant -- and with it the tracked minima -- identical everywhere."""
+    cap = int(os.environ.get('SHG_RECON_SM_CAP', '112'))
+    return (cap & 0xff) << 8
 
 
 # ----------------------------------------------------------------------------
@@ -346,7 +355,7 @@ def reconstruct_partial(stack, fit: np.ndarray, shifts, first_done=None):
         device_barrier()                   # every rank's rows of image 0 have landed on rank 0
         ready = torch.cuda.Event()
         ready.record()
-    eng.recon(stack, fit, shifts, disk=local, k0_out=h, mins=mins)
+    eng.recon(stack, fit, shifts, disk=local, k0_out=h, mins=mins, impl=_beside_fit() if split else 0)
     if not eng.recon_min_done:             # kernel variant without minimum tracking: one pass over the local rows
         mins = eng.minmax_device(local[:, h:h + n_local])[:, 0].contiguous()
     if split and rank == 0:
@@ -405,28 +414,103 @@ def broadcast_object(obj, src: int):
     return box[0]
 
 
+class _Mailbox:
+    """Twelve doubles in POSIX shared memory: [sequence number, status, nine geometry values, spare].  The ranks
+    of this package always share one box (frames are sharded over the GPUs of ONE node), so the ellipse geometry
+    can travel through host memory: the writer stores the payload, then the sequence number; the readers --
+    which have nothing else to do until the geometry exists -- poll the sequence number.  ~2 us instead of the
+    ~200 us of an NCCL broadcast bracketed by an upload and a blocking download."""
+
+    def __init__(self):
+        import atexit
+        from multiprocessing import shared_memory
+        rank, size = world()
+        name = None
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=12 * 8)
+            name = self.shm.name
+            atexit.register(self._unlink)
+        name = broadcast_object(name, 0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:                                            # the creator unlinks it; keep the tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
+        self.buf = np.ndarray((12,), dtype=np.float64, buffer=self.shm.buf)
+        if rank == 0:
+            self.buf[:] = 0.0
+        dist.barrier()                                      # zeroed before anybody polls
+        self.seq = 0
+
+    def _unlink(self):
+        try:
+            self.buf = None
+            self.shm.close()
+            self.shm.unlink()
+        except Exception:
+            pass
+
+    def post(self, vals10):
+        self.seq += 1
+        self.buf[1:11] = vals10
+        self.buf[0] = float(self.seq)                       # x86 keeps the store order: payload first
+
+    def take(self):
+        import time
+        self.seq += 1
+        want = float(self.seq)
+        spins = 0
+        while self.buf[0] < want:
+            spins += 1
+            if spins > 200:
+                time.sleep(2e-5)                            # (lets a worker thread of this process run)
+        return np.array(self.buf[1:11])
+
+
+_mailbox = None
+
+
+def _single_node() -> bool:
+    return int(os.environ.get('LOCAL_WORLD_SIZE', '0')) == int(os.environ.get('WORLD_SIZE', '-1'))
+
+
 def broadcast_geometry(geom, src: int = 0, error: BaseException | None = None):
     """The ellipse geometry (circle (cx, cy, r), ratio, phi, borders [4]) from the rank that fitted it to
-    all: nine doubles and a status word in ONE NCCL broadcast of a device tensor (broadcast_object_list
-    pickles and costs two broadcasts and two host synchronisations).  If the fit failed on `src`
-    (`error`), every rank raises instead of waiting in a collective for a result that will not come."""
+    all: nine doubles and a status word through a shared-memory mailbox (one node: the normal case) or in ONE
+    NCCL broadcast of a device tensor (broadcast_object_list pickles and costs two broadcasts and two host
+    synchronisations).  If the fit failed on `src` (`error`), every rank raises instead of waiting in a collective
+    for a result that will not come."""
+    global _mailbox
     rank, size = world()
     if size == 1:
         if error is not None:
             raise error
         return geom
-    dev = _comm_device()
     vals = np.zeros(10, dtype=np.float64)
     if rank == src:
         if error is None:
             circle, ratio, phi, borders = geom
             vals[:9] = [circle[0], circle[1], circle[2], ratio, phi] + [float(b) for b in borders]
             vals[9] = 1.0
-        t = get_engine().upload(vals) if dev.type == 'cuda' else torch.from_numpy(vals)
+    if src == 0 and _single_node() and (dist.get_backend() != 'gloo' or os.environ.get('SHG_GEOMETRY_MAILBOX')) \
+            and not os.environ.get('SHG_GEOMETRY_NCCL'):
+        if _mailbox is None:
+            _mailbox = _Mailbox()
+        if rank == 0:
+            _mailbox.post(vals)
+            v = vals
+        else:
+            v = _mailbox.take()
     else:
-        t = torch.empty((10,), dtype=torch.float64, device=dev)
-    dist.broadcast(t, src=src)
-    v = t.cpu().numpy()
+        dev = _comm_device()
+        if rank == src:
+            t = get_engine().upload(vals) if dev.type == 'cuda' else torch.from_numpy(vals)
+        else:
+            t = torch.empty((10,), dtype=torch.float64, device=dev)
+        dist.broadcast(t, src=src)
+        v = t.cpu().numpy()
     if v[9] != 1.0:
         if error is not None:
             raise error

@@ -130,54 +130,65 @@ def circularise_many(images, phi, ratio, prepared=None):
     return res, mat, mat3, theta
 
 
-def circularise_partial(parts, phi, ratio):
-    """Exchange mode 'post_warp' (parallel.py): every rank warps ITS frames of every image in `parts`
-    (device_image.PartialImage, all slices of one local buffer) and stores the pixels it produces straight
-    into the rank that owns the image (peer memory).  Returns a list with a row-major DeviceImage for the
-    images this rank owns and None for the others; owners are assigned by position in the list."""
+def prepare_partial(parts):
+    """The geometry-independent half of circularise_partial: which slice of the local buffer each image is, the
+    launch order, clip ranges and fill constants on the device.  Called before the ellipse geometry is known (while
+    rank 0 fits it), so that nothing but the warp plan stands between the broadcast and the launch."""
     from . import parallel
     eng = get_engine()
     rank, size = parallel.world()
-    prep = eng.stage('circ_prep')
-    prep.__enter__()
+    with eng.stage('circ_prep'):
+        p0 = parts[0]
+        flip = p0.flip
+        n_ext, ih = p0.tensor.shape
+        stride = n_ext * ih
+        base_ptr = min(p.tensor.data_ptr() for p in parts)
+        first = min(parts, key=lambda p: p.tensor.data_ptr()).tensor
+        idx = []
+        for p in parts:
+            off = (p.tensor.data_ptr() - base_ptr) // 2
+            assert off % stride == 0 and p.tensor.is_contiguous() and p.flip == flip and p.tensor.shape == p0.tensor.shape
+            idx.append(off // stride)
+        base = torch.as_strided(first, (max(idx) + 1, n_ext, ih), (stride, ih, 1))
+        owner = parallel.shift_owner(len(parts), size, 'by_shift')
+        # Launch order of the images (blockIdx.z): every rank starts with the images of the NEXT rank and goes
+        # round, so that at any moment the ranks store into different owners.  In list order all ranks wrote into
+        # rank 0's memory first, then all into rank 1's, ...: the owner's NVLink ingress was the bottleneck and
+        # everybody else's egress idled (measured at four GPUs: 3.6 - 4.1 ms for this step instead of 2.3).
+        order = sorted(range(len(parts)), key=lambda q: ((owner[q] - rank - 1) % size, q))
+        mins, red = p0.min_ref[0], p0.cval_ref[0]
+        assert all(p.min_ref[0].data_ptr() == mins.data_ptr() and p.cval_ref[0].data_ptr() == red.data_ptr() for p in parts)
+        src = eng.upload(np.asarray([parts[q].min_ref[1] for q in order], dtype=np.int64))
+        mm = torch.empty((len(parts), 2), dtype=torch.int32, device=eng.device)
+        mm[:, 0] = mins[src]
+        mm[:, 1] = 65535
+        cvals = red[2 if flip else 1][src].contiguous()              # image[0][0]: last / first physical frame
+        sel = eng.upload(np.asarray([idx[q] for q in order], dtype=np.int32))
+    return dict(base=base, order=order, sel=sel, mm=mm, cvals=cvals, owner=owner)
+
+
+def circularise_partial(parts, phi, ratio, prepared=None):
+    """Exchange mode 'post_warp' (parallel.py): every rank warps ITS frames of every image in `parts`
+    (device_image.PartialImage, all slices of one local buffer) into a local full-width image and copies the
+    pixels it produced into the rank that owns the image (peer memory).  Returns a list with a row-major
+    DeviceImage for the images this rank owns and None for the others; owners are assigned by position in the list."""
+    from . import parallel
+    eng = get_engine()
+    rank, size = parallel.world()
+    prep = prepared if prepared is not None else prepare_partial(parts)
     p0 = parts[0]
     ih, n_frames = p0.shape
     flip = p0.flip
     mat, mat3, out_shape, _, theta = geometry.warp_plan((ih, n_frames), phi, ratio)
     oh, ow = int(out_shape[0]), int(out_shape[1])
     ex = parallel.circ_exchange(len(parts), oh, ow)
-    # all parts are slices of the (S, halo + n_local + halo, ih) buffer of parallel.reconstruct_partial
-    n_ext = p0.tensor.shape[0]
-    stride = n_ext * ih
-    base_ptr = min(p.tensor.data_ptr() for p in parts)
-    first = min(parts, key=lambda p: p.tensor.data_ptr()).tensor
-    idx = []
-    for p in parts:
-        off = (p.tensor.data_ptr() - base_ptr) // 2
-        assert off % stride == 0 and p.tensor.is_contiguous() and p.flip == flip and p.tensor.shape == p0.tensor.shape
-        idx.append(off // stride)
-    base = torch.as_strided(first, (max(idx) + 1, n_ext, ih), (stride, ih, 1))
-    mins, red = p0.min_ref[0], p0.cval_ref[0]
-    # Launch order of the images (blockIdx.z): every rank starts with the images of the NEXT rank and goes round,
-    # so that at any moment the ranks store into different owners.  In list order all ranks wrote into rank 0's
-    # memory first, then all into rank 1's, ...: the owner's NVLink ingress was the bottleneck and everybody
-    # else's egress idled (measured at four GPUs: 3.6 - 4.1 ms for this launch instead of 1.7).
-    order = sorted(range(len(parts)), key=lambda q: ((ex.owner[q] - rank - 1) % size, q))
     if getattr(ex, 'ptrs_rot', None) is None:
-        ex.ptrs_rot = eng.upload(ex.ptrs.view(np.int64)[order]).view(torch.int64)
-    idx = [idx[q] for q in order]
-    src = eng.upload(np.asarray([parts[q].min_ref[1] for q in order], dtype=np.int64))
-    assert all(p.min_ref[0].data_ptr() == mins.data_ptr() and p.cval_ref[0].data_ptr() == red.data_ptr() for p in parts)
-    mm = torch.empty((len(parts), 2), dtype=torch.int32, device=eng.device)
-    mm[:, 0] = mins[src]
-    mm[:, 1] = 65535
-    cvals = red[2 if flip else 1][src].contiguous()                  # image[0][0]: last / first physical frame
+        ex.ptrs_rot = eng.upload(ex.ptrs.view(np.int64)[prep['order']]).view(torch.int64)
     own_lo, own_hi = parallel.owned_logical_frames(n_frames, rank, size, flip)
-    prep.__exit__()
     parallel.device_barrier()              # the owners are done reading the previous scan's circularised images
     with eng.stage('warp'):
-        eng.warp_batch(base, idx, flip, mat3, (oh, ow), mm, n_frames=n_frames, frame_origin=p0.k0 - p0.halo,
-                       cvals=cvals, window=(own_lo, own_hi), out_ptrs=ex.ptrs_rot)
+        eng.warp_batch(prep['base'], prep['sel'], flip, mat3, (oh, ow), prep['mm'], n_frames=n_frames,
+                       frame_origin=p0.k0 - p0.halo, cvals=prep['cvals'], window=(own_lo, own_hi), out_ptrs=ex.ptrs_rot)
     parallel.device_barrier()              # every rank's pixels have landed
     out = [None] * len(parts)
     for n, q in enumerate(ex.mine):

@@ -81,6 +81,22 @@ def _worker(rank, world, port, out_dir):
         else:
             raise AssertionError('a failed fit must raise on every rank')
         parallel.device_barrier()
+        # the same through the shared-memory mailbox the GPU runs use on one node (several rounds: sequence numbers)
+        os.environ.update(LOCAL_WORLD_SIZE=str(world), SHG_GEOMETRY_MAILBOX='1')
+        for rnd in range(3):
+            w2 = ((want[0][0] + rnd, want[0][1], want[0][2]), want[1], want[2] * (rnd + 1), want[3])
+            got = parallel.broadcast_geometry(w2 if rank == 0 else None, 0)
+            assert got == w2, (rnd, got)
+        try:
+            parallel.broadcast_geometry(None, 0, ValueError('no edges') if rank == 0 else None)
+        except ValueError:
+            assert rank == 0
+        except Exception as e:
+            assert rank != 0 and 'rank 0' in str(e)
+        else:
+            raise AssertionError('a failed fit must raise on every rank')
+        assert parallel._mailbox is not None
+        dist.barrier()
         open(os.path.join(out_dir, 'ok%d' % rank), 'w').write('ok')
     finally:
         dist.destroy_process_group()
