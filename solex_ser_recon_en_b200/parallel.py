@@ -415,58 +415,51 @@ def broadcast_object(obj, src: int):
 
 
 class _Mailbox:
-    """Twelve doubles in POSIX shared memory: [sequence number, status, nine geometry values, spare].  The ranks
-    of this package always share one box (frames are sharded over the GPUs of ONE node), so the ellipse geometry
-    can travel through host memory: the writer stores the payload, then the sequence number; the readers --
-    which have nothing else to do until the geometry exists -- poll the sequence number.  ~2 us instead of the
-    ~200 us of an NCCL broadcast bracketed by an upload and a blocking download."""
+    """A ring of eight 12-double slots in a shared mapping (a file in /dev/shm, unlinked once every rank has mapped
+    it): slot = [sequence number, status + nine geometry values, spare].  The ranks of this package always share one
+    box (frames are sharded over the GPUs of ONE node), so the ellipse geometry can travel through host memory: the
+    writer fills slot seq % 8, then stores the sequence number; the readers -- which have nothing else to do until
+    the geometry exists -- poll it.  ~2 us instead of the ~200 us of an NCCL broadcast bracketed by an upload and a
+    blocking download.  (The writer cannot lap a reader by eight scans: every scan has collectives.)"""
+    SLOTS = 8
 
     def __init__(self):
-        import atexit
-        from multiprocessing import shared_memory
+        import mmap
+        import tempfile
         rank, size = world()
-        name = None
+        path = None
+        nbytes = self.SLOTS * 12 * 8
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=12 * 8)
-            name = self.shm.name
-            atexit.register(self._unlink)
-        name = broadcast_object(name, 0)
-        if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name)
-            try:                                            # the creator unlinks it; keep the tracker out of it
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self.shm._name, 'shared_memory')
-            except Exception:
-                pass
-        self.buf = np.ndarray((12,), dtype=np.float64, buffer=self.shm.buf)
+            base = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+            fd, path = tempfile.mkstemp(prefix='shg_geometry_', dir=base)
+            os.write(fd, bytes(nbytes))
+            os.close(fd)
+        path = broadcast_object(path, 0)
+        with open(path, 'r+b') as f:
+            self.map = mmap.mmap(f.fileno(), nbytes)
+        self.buf = np.frombuffer(self.map, dtype=np.float64).reshape(self.SLOTS, 12)
+        dist.barrier()                                      # everybody has it mapped: the name can go
         if rank == 0:
-            self.buf[:] = 0.0
-        dist.barrier()                                      # zeroed before anybody polls
+            os.unlink(path)
         self.seq = 0
-
-    def _unlink(self):
-        try:
-            self.buf = None
-            self.shm.close()
-            self.shm.unlink()
-        except Exception:
-            pass
 
     def post(self, vals10):
         self.seq += 1
-        self.buf[1:11] = vals10
-        self.buf[0] = float(self.seq)                       # x86 keeps the store order: payload first
+        slot = self.buf[self.seq % self.SLOTS]
+        slot[1:11] = vals10
+        slot[0] = float(self.seq)                           # x86 keeps the store order: payload first
 
     def take(self):
         import time
         self.seq += 1
+        slot = self.buf[self.seq % self.SLOTS]
         want = float(self.seq)
         spins = 0
-        while self.buf[0] < want:
+        while slot[0] != want:
             spins += 1
             if spins > 200:
                 time.sleep(2e-5)                            # (lets a worker thread of this process run)
-        return np.array(self.buf[1:11])
+        return np.array(slot[1:11])
 
 
 _mailbox = None
