@@ -14,6 +14,8 @@
 // Outputs are tiny (order statistics, 20 counts, a list of thin-edge pixels);
 // labelling, convex hull and the 6-parameter ellipse fit stay on the host.
 // All kernels are O(rows*cols) over a ~5 Mpx image: microseconds each.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -343,6 +345,127 @@ blur_hist_dev_kernel(const uint32_t* __restrict__ box, int64_t n, double scale, 
     if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(&st->counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
 
+// ---------------------------------------------------------------------------
+// Fused canny front (shg_limb_canny): two kernels instead of seven, same arithmetic in the same order.
+//  K1 flood_gauss_kernel: flood image made on the fly from the box sums, gaussian along axis 0 then axis 1 through
+//     shared memory, the same for the all-ones mask, and the division -- one pass over the image instead of five
+//     (four 17-tap passes over 40 MB images of doubles + the divide).
+//  K2 sobel_nms_kernel: Sobel at the pixel; only where the magnitude reaches `low` (a few per cent of the image:
+//     the flood image is flat away from the limb) the four neighbour magnitudes the interpolated non-maximum
+//     suppression needs are evaluated -- no gi / gj / magnitude images are written at all.
+constexpr int kGT_H = 16, kGT_W = 64;
+
+__global__ void __launch_bounds__(256)
+flood_gauss_kernel(const uint32_t* __restrict__ box, int rows, int cols, double scale, double level, const GaussW g,
+                   double eps, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int R = g.radius;
+    const int fw = kGT_W + 2 * R, fh = kGT_H + 2 * R;
+    double* a = reinterpret_cast<double*>(sm_raw);                 // [kGT_H][fw]   axis-0 result of the flood image
+    double* a1row = a + kGT_H * fw;                                // [kGT_H]       axis-0 result of the ones mask
+    unsigned char* f = reinterpret_cast<unsigned char*>(a1row + kGT_H);   // [fh][fw]  bit0: flood on, bit1: inside
+    const int r0 = blockIdx.y * kGT_H, c0 = blockIdx.x * kGT_W;
+    for (int i = threadIdx.x; i < fh * fw; i += 256) {
+        const int rr = i / fw, cc = i - rr * fw;
+        const int gr = r0 - R + rr, gc = c0 - R + cc;
+        unsigned char v = 0;
+        if (gr >= 0 && gr < rows && gc >= 0 && gc < cols)
+            v = 2 | (blurred_of(box[(int64_t)gr * cols + gc], scale) < level ? 0 : 1);
+        f[i] = v;
+    }
+    __syncthreads();
+    // axis 0 (rows): in[0]*w[0] + sum_{k = R..1} (in[-k] + in[+k]) * w[k]
+    for (int i = threadIdx.x; i < kGT_H * fw; i += 256) {
+        const int rr = i / fw, cc = i - rr * fw;
+        const unsigned char* col = f + (rr + R) * fw + cc;
+        double acc = __dmul_rn((col[0] & 1) ? 65000.0 : 0.0, g.w[0]);
+        for (int k = R; k >= 1; --k) {
+            const double pair = __dadd_rn((col[-k * fw] & 1) ? 65000.0 : 0.0, (col[k * fw] & 1) ? 65000.0 : 0.0);
+            acc = __dadd_rn(acc, __dmul_rn(pair, g.w[k]));
+        }
+        a[i] = acc;
+    }
+    if (threadIdx.x < kGT_H) {
+        const int gr = r0 + threadIdx.x;
+        double acc = __dmul_rn((gr < rows) ? 1.0 : 0.0, g.w[0]);
+        for (int k = R; k >= 1; --k) {
+            const double pair = __dadd_rn((gr - k >= 0 && gr - k < rows) ? 1.0 : 0.0, (gr + k < rows && gr + k >= 0) ? 1.0 : 0.0);
+            acc = __dadd_rn(acc, __dmul_rn(pair, g.w[k]));
+        }
+        a1row[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    // axis 1 (columns) of both, then the division
+    for (int i = threadIdx.x; i < kGT_H * kGT_W; i += 256) {
+        const int rr = i / kGT_W, cc = i - rr * kGT_W;
+        const int gr = r0 + rr, gc = c0 + cc;
+        if (gr >= rows || gc >= cols) continue;
+        const double* arow = a + rr * fw + cc + R;
+        const double one = a1row[rr];
+        double b = __dmul_rn(arow[0], g.w[0]);
+        double b1 = __dmul_rn(one, g.w[0]);
+        for (int k = R; k >= 1; --k) {
+            b = __dadd_rn(b, __dmul_rn(__dadd_rn(arow[-k], arow[k]), g.w[k]));
+            const double pair1 = __dadd_rn(gc - k >= 0 ? one : 0.0, gc + k < cols ? one : 0.0);
+            b1 = __dadd_rn(b1, __dmul_rn(pair1, g.w[k]));
+        }
+        out[(int64_t)gr * cols + gc] = __ddiv_rn(b, __dadd_rn(b1, eps));
+    }
+}
+
+struct SobelOut { double gi, gj, mag; };
+
+__device__ __forceinline__ SobelOut sobel_at(const double* __restrict__ s, int rows, int cols, int r, int c) {
+    auto S = [&](int rr, int cc) { return s[(int64_t)reflect_edge(rr, rows) * cols + reflect_edge(cc, cols)]; };
+    auto d1 = [&](int rr, int cc) {
+        return __dadd_rn(__dmul_rn(S(rr, cc), 0.0), __dmul_rn(__dsub_rn(S(rr, cc - 1), S(rr, cc + 1)), -1.0));
+    };
+    auto d0 = [&](int rr, int cc) {
+        return __dadd_rn(__dmul_rn(S(rr, cc), 0.0), __dmul_rn(__dsub_rn(S(rr - 1, cc), S(rr + 1, cc)), -1.0));
+    };
+    auto D1 = [&](int rr, int cc) { return d1(reflect_edge(rr, rows), reflect_edge(cc, cols)); };
+    auto D0 = [&](int rr, int cc) { return d0(reflect_edge(rr, rows), reflect_edge(cc, cols)); };
+    SobelOut o;
+    o.gj = __dadd_rn(__dmul_rn(D1(r, c), 2.0), __dmul_rn(__dadd_rn(D1(r - 1, c), D1(r + 1, c)), 1.0));
+    o.gi = __dadd_rn(__dmul_rn(D0(r, c), 2.0), __dmul_rn(__dadd_rn(D0(r, c - 1), D0(r, c + 1)), 1.0));
+    o.mag = __dsqrt_rn(__dadd_rn(__dmul_rn(o.gi, o.gi), __dmul_rn(o.gj, o.gj)));
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+sobel_nms_kernel(const double* __restrict__ s, int rows, int cols, double low, unsigned int* __restrict__ count,
+                 unsigned int cap, uint32_t* __restrict__ list_idx, double* __restrict__ list_mag) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx % cols);
+    if (r < 1 || r >= rows - 1 || c < 1 || c >= cols - 1) return;          // eroded mask
+    const SobelOut me = sobel_at(s, rows, cols, r, c);
+    const double m = me.mag;
+    if (!(m >= low)) return;
+    const double a = me.gi, b = me.gj;
+    const double aa = fabs(a), ab = fabs(b);
+    const bool same = (a >= 0 && b >= 0) || (a <= 0 && b <= 0);
+    const bool opp = (a <= 0 && b >= 0) || (a >= 0 && b <= 0);
+    if (!(same || opp)) return;                                             // nan gradients
+    int d1i, d1j, d2i, d2j;
+    double w;
+    if (same) {
+        if (aa > ab) { d1i = 1; d1j = 0; d2i = 1; d2j = 1; w = __ddiv_rn(ab, aa); }
+        else         { d1i = 0; d1j = 1; d2i = 1; d2j = 1; w = __ddiv_rn(aa, ab); }
+    } else {
+        if (aa < ab) { d1i = 0; d1j = 1; d2i = -1; d2j = 1; w = __ddiv_rn(aa, ab); }
+        else         { d1i = -1; d1j = 0; d2i = -1; d2j = 1; w = __ddiv_rn(ab, aa); }
+    }
+    auto M = [&](int di, int dj) { return sobel_at(s, rows, cols, r + di, c + dj).mag; };
+    const double omw = __dsub_rn(1.0, w);
+    const double plus = __dadd_rn(__dmul_rn(M(d2i, d2j), w), __dmul_rn(M(d1i, d1j), omw));
+    const double minus = __dadd_rn(__dmul_rn(M(-d2i, -d2j), w), __dmul_rn(M(-d1i, -d1j), omw));
+    if (plus <= m && minus <= m && m > 0.0) {
+        const unsigned int slot = atomicAdd(count, 1u);
+        if (slot < cap) { list_idx[slot] = (uint32_t)idx; list_mag[slot] = m; }
+    }
+}
+
 unsigned grid_for(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256), 148 * 16)); }
 
 }  // namespace
@@ -530,13 +653,29 @@ extern "C" int shg_limb_canny(const uint32_t* d_box, int rows, int cols, double 
     const int64_t n = (int64_t)rows * cols;
     cudaStream_t st = as_stream(stream);
     double* smoothed = d_buf6;
-    int rc = shg_flood_smooth(d_box, rows, cols, scale, level, h_weights, radius, eps, smoothed, d_buf6 + n, stream);
-    if (rc) return rc;
-    rc = shg_sobel_mag(smoothed, rows, cols, d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, stream);
-    if (rc) return rc;
-    rc = shg_nms_candidates(d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, rows, cols, low, d_count, cap, d_list_idx,
-                            d_list_mag, stream);
-    if (rc) return rc;
+    SHG_REQUIRE(radius >= 0 && radius <= 32, "shg_limb_canny: radius %d (max 32)", radius);
+    if (getenv("SHG_LIMB_UNFUSED")) {                           // the seven-kernel formulation (cross-check / timing)
+        int rc = shg_flood_smooth(d_box, rows, cols, scale, level, h_weights, radius, eps, smoothed, d_buf6 + n, stream);
+        if (rc) return rc;
+        rc = shg_sobel_mag(smoothed, rows, cols, d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, stream);
+        if (rc) return rc;
+        rc = shg_nms_candidates(d_buf6 + 3 * n, d_buf6 + 4 * n, d_buf6 + 5 * n, rows, cols, low, d_count, cap, d_list_idx,
+                                d_list_mag, stream);
+        if (rc) return rc;
+    } else {
+        GaussW g;
+        for (int k = 0; k <= radius; ++k) g.w[k] = h_weights[k];
+        g.radius = radius;
+        const int fw = kGT_W + 2 * radius, fh = kGT_H + 2 * radius;
+        const size_t smem = (size_t)(kGT_H * fw + kGT_H) * sizeof(double) + (size_t)fh * fw;
+        SHG_CHECK(cudaFuncSetAttribute(flood_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        flood_gauss_kernel<<<dim3((cols + kGT_W - 1) / kGT_W, (rows + kGT_H - 1) / kGT_H), 256, smem, st>>>(
+            d_box, rows, cols, scale, level, g, eps, smoothed);
+        SHG_CHECK(cudaMemsetAsync(d_count, 0, 4, st));
+        sobel_nms_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(smoothed, rows, cols, low, d_count, cap, d_list_idx,
+                                                                     d_list_mag);
+        SHG_LAUNCH_CHECK();
+    }
     // the count and the head of the list travel together: one round trip for the usual ~10^4 candidates
     const uint32_t head = std::min(first_chunk, cap);
     SHG_CHECK(cudaMemcpyAsync(h_count, d_count, 4, cudaMemcpyDeviceToHost, st));
