@@ -677,16 +677,24 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
                         const int32_t* __restrict__ xb_list, int n_list,
                         double* __restrict__ out,
-                        double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap, int use_hist) {
+                        double* __restrict__ gscratch, int64_t scratch_pitch, int smem_cap, int use_hist,
+                        const uint32_t* __restrict__ todo, const unsigned int* __restrict__ todo_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& S = *reinterpret_cast<Shared*>(smem_raw);
     LogSeg* seg = reinterpret_cast<LogSeg*>(smem_raw + kSharedBytes);
-    double* vals = reinterpret_cast<double*>(smem_raw + kHeadBytes);
+    double* const vals_shared = reinterpret_cast<double*>(smem_raw + kHeadBytes);
     for (int h = threadIdx.x; h < 128; h += kT) seg[h] = g_logseg[h];
     __syncthreads();
-    const int j = blockIdx.x;
-    const int64_t slot = (int64_t)blockIdx.y * n_list + j;          // (image, row) result index
-    const uint16_t* img = img_base + (int64_t)blockIdx.y * img_stride;
+    // Two launch shapes: grid (n_list, n_imgs), one CTA per (row, image); or, with a todo list (the rows the
+    // register-resident kernel below handed back), a small persistent grid that walks the list.
+    const bool listed = todo != nullptr;
+    int64_t work = listed ? (int64_t)blockIdx.x : (int64_t)blockIdx.y * n_list + blockIdx.x;
+    const int64_t work_end = listed ? (int64_t)*todo_count : work + 1;
+    const int64_t work_step = listed ? (int64_t)gridDim.x : 1;
+    auto one_row = [&](const int64_t slot) {
+    const int j = (int)(slot % n_list);
+    const uint16_t* img = img_base + (slot / n_list) * img_stride;
+    double* vals = vals_shared;
     const int y = rows[j], xa = xa_list[j], xb = xb_list[j];
     const int n = xb - xa;
     if (n <= 0) {                                   // np.mean of an empty slice
@@ -837,6 +845,393 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
     double cnt = (double)kept;
     block_sum2(sum, cnt, S);
     if (threadIdx.x == 0) out[slot] = sum / cnt;
+    };
+    for (; work < work_end; work += work_step) {
+        one_row(listed ? (int64_t)todo[work] : work);
+        __syncthreads();                             // shared state is reused by the next row
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident row statistics (the launch every real scan takes).
+// A thread keeps its E = 16 ratios in REGISTERS (element e of thread t is chord position e*kT + t), so the
+// passes after the first are straight-line code with no shared-memory traffic for the values, and shared
+// memory (7 KB) no longer limits residency: 4 CTAs of 256 threads per SM at <= 64 registers.
+//   pass 1  ratios + 1024-bin counts (bins from sample quartiles, as above); block scan -> prefix table P
+//   pass 2  WINDOW SELECT for the median: the value window [lo, hi) of the bin(s) holding the middle ranks;
+//           every thread counts its values below the window and appends those inside to a list; the list is
+//           ranked exactly in fp64.  The counts are taken from the data, so the result does not depend on
+//           the bin arithmetic being consistent with the window edges: if the middle ranks do not fall in
+//           the list (an edge rounding, a list overflow) the row is handed back.
+//   pass 3  WINDOW SELECT for the MAD without a second histogram: with u = position of the median in bin
+//           units, the values with |r - med| < k bins lie in bins floor(u)-k .. floor(u)+k, and all values of
+//           bins floor(u)-k+1 .. floor(u)+k-1 are that close, so P brackets the count for every k: the
+//           largest k_lo with upper(k_lo) <= t0 and the smallest k_hi with lower(k_hi) > t1 (two ballots
+//           each) give a distance window [k_lo w, k_hi w) that holds both middle ranks; same count / collect
+//           / verify / rank as pass 2, on the keys |r - med|.
+//   pass 4  mean of the inliers, in the same per-thread order and with the same block reduction as the
+//           classic kernel (identical bits: test_row_stats_counting_select_equals_bitsliced).
+// Rows this cannot take (a zero pixel, chords <= 256 or > 16 kT, ties that overflow a list, an
+// unrepresentative sample, MAD == 0) are appended to a todo list and done by the classic kernel above.
+constexpr int kBins2 = 2048;
+constexpr int kCap2 = 128;            // candidate list (a few dozen with bins this fine)
+constexpr int kMinLen2 = 256;         // shorter chords: the classic kernel ranks everything
+
+template <int kT>
+struct Shared2 {
+    // counts; after the scan the exclusive prefix, entry kBins2 = n.  Bin b lives at H[b + b / (bins per thread)]:
+    // the scan gives a thread consecutive bins, and the padding word makes its stride odd (no bank conflicts)
+    unsigned int H[kBins2 + kT + 8];
+    double list[kCap2];
+    double red[32];
+    unsigned int wsum[32];
+    double dbc[4];
+    int ibc[4];
+    int list_n, below, kept;
+};
+
+// Bins of the register-resident kernel: kBins2 - 2 regular bins over the sample's inter-quartile range widened by
+// 3 IQR each side (a 32-value sample can misjudge the spread by a factor of two and med +- MAD still lies inside;
+// whatever falls outside goes to the two open bins), i.e. a bin is IQR/292 wide: a handful of values per bin at the centre of a 3000-pixel chord.
+struct HistBins2 {
+    double lo, scale, magic, width;
+    __device__ __forceinline__ void set(double qlo, double qhi) {
+        const double iqr = qhi - qlo;
+        lo = qlo - 3.0 * iqr;
+        scale = (double)(kBins2 - 2) / (7.0 * iqr);
+        width = iqr * (7.0 / (double)(kBins2 - 2));
+        magic = 6755399441055744.0 + 1.0;
+    }
+    __device__ __forceinline__ int operator()(double x) const {
+        const int b = __double2loint(__fma_rd(x - lo, scale, magic));
+        return min(max(b, 0), kBins2 - 1);
+    }
+};
+
+// ranks t0, t1 of the multiset {`below` smaller values} + list[0..mm) -> dbc[0], dbc[1].  P = 2^k threads share one
+// candidate (each counts a slice of the list, the partial ranks meet by shuffles), so a list of 100 costs a few
+// dozen iterations on every warp instead of 100 on three of them while the others wait.
+template <int kT>
+__device__ __forceinline__ void rank_list2(Shared2<kT>& S, int mm, int below, int t0, int t1) {
+    if (mm <= 32) {                                    // the usual case: a lane per list entry, a ballot per candidate
+        const int lane = threadIdx.x & 31;
+        const double mine = lane < mm ? S.list[lane] : INFINITY;
+        for (int c = threadIdx.x >> 5; c < mm; c += kT / 32) {          // (uniform per warp)
+            const double x = __shfl_sync(0xffffffffu, mine, c);
+            const bool before = lane < mm && (mine < x || (mine == x && lane < c));
+            const int rank = below + __popc(__ballot_sync(0xffffffffu, before));
+            if (lane == 0) {
+                if (rank == t0) S.dbc[0] = x;
+                if (rank == t1) S.dbc[1] = x;
+            }
+        }
+        return;
+    }
+    int lg = 0;
+    while (lg < 5 && (mm << (lg + 1)) <= kT) ++lg;     // (uniform)
+    const int P = 1 << lg;
+    const int p = threadIdx.x & (P - 1);
+    const int chunk = (mm + P - 1) >> lg;
+    const int j0 = p * chunk, j1 = min(mm, j0 + chunk);
+    for (int c0 = 0; c0 < mm; c0 += kT >> lg) {        // (uniform trip count)
+        const int c = c0 + ((int)threadIdx.x >> lg);
+        const double x = S.list[min(c, mm - 1)];
+        int rank = 0;
+#pragma unroll 4
+        for (int i = j0; i < j1; ++i) {
+            const double o = S.list[i];
+            rank += (o < x || (o == x && i < c)) ? 1 : 0;
+        }
+        for (int o = P >> 1; o; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        rank += below;
+        if (c < mm && p == 0) {
+            if (rank == t0) S.dbc[0] = x;
+            if (rank == t1) S.dbc[1] = x;
+        }
+    }
+}
+
+// the rare pairs outside the series' range (inlined: a call makes the compiler spill the register-resident values)
+__device__ __forceinline__ double log_ratio_far(uint32_t a, uint32_t b) {
+    return log_u16(a, g_logseg) - log_u16(b, g_logseg);
+}
+
+template <int kT>
+__device__ __forceinline__ void list_append2(Shared2<kT>& S, double k) {
+    const int at = atomicAdd(&S.list_n, 1);
+    if (at < kCap2) S.list[at] = k;
+}
+
+// ER chord positions per thread in registers, up to ES more in shared memory (position e of thread t is chord
+// index e*kT + t; spill[(e - ER)*kT + t]).
+template <int kT, int ER, int ES>
+__global__ void __launch_bounds__(kT, (1024 / kT > 0 ? 1024 / kT : 1))
+transv_row_stats_reg_kernel(const uint16_t* __restrict__ img_base, int64_t img_stride, int cols,
+                            const int32_t* __restrict__ rows, const int32_t* __restrict__ xa_list,
+                            const int32_t* __restrict__ xb_list, int n_list, double* __restrict__ out,
+                            uint32_t* __restrict__ todo, unsigned int* __restrict__ todo_count, int stop) {
+    __shared__ Shared2<kT> S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* const spill = reinterpret_cast<double*>(smem_raw);
+    constexpr int G = 2;                              // elements per group: one uniform guard, two interleaved chains
+                                                      // (four spill: the values must stay in registers)
+    constexpr int NG = ER / G;
+    constexpr int NW = kT / 32;
+    constexpr int kDump = kBins2 + 2;                 // counts of the padding lanes go here (beyond the scan)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = blockIdx.x;
+    const int64_t slot = (int64_t)blockIdx.y * n_list + j;
+    const int y = rows[j], xa = xa_list[j];
+    const int n = xb_list[j] - xa;
+    auto defer = [&](int why) {                       // (uniform) hand the row back; todo_count[why] counts the reasons
+        if (tid == 0) {
+            todo[atomicAdd(todo_count, 1u)] = (uint32_t)slot;
+            atomicAdd(todo_count + why, 1u);
+        }
+    };
+    if (n <= kMinLen2 || n > kT * (ER + ES)) { defer(1); return; }
+    const uint16_t* img = img_base + (int64_t)blockIdx.y * img_stride;
+    const uint16_t* ry = img + (int64_t)y * cols + xa;
+    const uint16_t* rp = img + (int64_t)(y - 1) * cols + xa;
+    const int n_groups = (n + G * kT - 1) / (G * kT);          // groups of G positions per thread that hold any pixel
+
+    // pixels of the first group are in flight while warp 0 looks at the sample
+    uint32_t na[G], nb[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const int i = u * kT + tid;
+        na[u] = i < n ? (uint32_t)__ldg(ry + i) : 1u;
+        nb[u] = i < n ? (uint32_t)__ldg(rp + i) : 1u;
+    }
+    // bin edges from the quartiles of 32 sample ratios (warp 0)
+    if (warp == 0) {
+        const int i = (int)(((int64_t)(2 * lane + 1) * n) >> 6);
+        const double x = log_ratio_u16(__ldg(ry + i), __ldg(rp + i), g_logseg);
+        S.list[lane] = x;
+        __syncwarp();
+        int rank = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const double o = S.list[q];
+            rank += (o < x || (o == x && q < lane)) ? 1 : 0;
+        }
+        if (rank == 8) S.dbc[2] = x;
+        if (rank == 23) S.dbc[3] = x;
+    }
+    constexpr int BPT = kBins2 / kT;                  // bins per thread in the scan
+    static_assert(BPT >= 2 && BPT * kT == kBins2 && (BPT & (BPT - 1)) == 0, "thread count must divide the bin count");
+    constexpr int kPadShift = BPT == 2 ? 1 : (BPT == 4 ? 2 : (BPT == 8 ? 3 : (BPT == 16 ? 4 : 5)));
+    static_assert((1 << kPadShift) == BPT, "2 to 32 bins per thread");
+    auto pad = [](int b) { return b + (b >> kPadShift); };
+    for (int q = tid; q < kBins2 + kT; q += kT) S.H[q] = 0;
+    if (tid == 0) { S.list_n = 0; S.below = 0; S.kept = 0; }
+    __syncthreads();
+    const double qlo = S.dbc[2], qhi = S.dbc[3];
+    if (!hist_usable(n, qlo, qhi)) { defer(2); return; }
+    if (stop == 1) return;                            // (timing knob SHG_TRANSV_STOP: cost of the phases)
+    HistBins2 bin0;
+    bin0.set(qlo, qhi);
+
+    // ---- pass 1: ratios + counts ----------------------------------------------------------------------
+    double v[ER];
+    bool bad = false;
+    // one group: the pixels that were in flight, the next group's loads, four series, the rare redo, counts
+    auto ratios_of_group = [&](const int g, double (&r)[G]) {
+        uint32_t ca[G], cb[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) { ca[u] = na[u]; cb[u] = nb[u]; }
+        if (g + 1 < n_groups) {                                // (uniform)
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const int i = ((g + 1) * G + u) * kT + tid;
+                na[u] = i < n ? (uint32_t)__ldg(ry + i) : 1u;
+                nb[u] = i < n ? (uint32_t)__ldg(rp + i) : 1u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) r[u] = log_ratio_series(ca[u], cb[u]);
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            if (!log_ratio_small(ca[u], cb[u])) {              // limb, dust, zeros
+                r[u] = log_ratio_far(ca[u], cb[u]);
+                bad |= !(fabs(r[u]) < INFINITY);               // a zero pixel: the classic kernel knows the rules
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const bool valid = (g * G + u) * kT + tid < n;
+            atomicAdd(&S.H[pad(valid ? bin0(r[u]) : kDump)], 1u);
+            r[u] = valid ? r[u] : NAN;                         // padding fails every comparison below
+        }
+    };
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int u = 0; u < G; ++u) v[g * G + u] = NAN;
+        if (g < n_groups) {                                    // (uniform)
+            double r[G];
+            ratios_of_group(g, r);
+#pragma unroll
+            for (int u = 0; u < G; ++u) v[g * G + u] = r[u];
+        }
+    }
+    if constexpr (ES > 0) {
+#pragma unroll 1
+        for (int g = NG; g < n_groups; ++g) {
+            double r[G];
+            ratios_of_group(g, r);
+#pragma unroll
+            for (int u = 0; u < G; ++u) spill[((g - NG) * G + u) * kT + tid] = r[u];
+        }
+    }
+    if (__syncthreads_or(bad)) { defer(3); return; }
+    if (stop == 2) { if (v[0] == 1.25) out[slot] = v[ER - 1]; return; }
+    // every value of this thread, in chord order: f(value)
+    auto for_each_value = [&](auto f) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (g < n_groups) {                                // (uniform)
+#pragma unroll
+                for (int u = 0; u < G; ++u) f(v[g * G + u]);
+            }
+        }
+        if constexpr (ES > 0) {
+#pragma unroll 1
+            for (int g = NG; g < n_groups; ++g) {
+                double r[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) r[u] = spill[((g - NG) * G + u) * kT + tid];
+#pragma unroll
+                for (int u = 0; u < G; ++u) f(r[u]);
+            }
+        }
+    };
+
+    // ---- exclusive scan of the counts, in place; the bins of the middle ranks ---------------------------
+    const int t0 = (n - 1) / 2, t1 = n / 2;
+    {
+        unsigned int* mine_h = &S.H[tid * (BPT + 1)];           // == &S.H[pad(tid * BPT)]
+        unsigned int s = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) s += mine_h[q];
+        unsigned int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) S.wsum[warp] = inc;
+        __syncthreads();
+        unsigned int run = inc - s;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) run += w < warp ? S.wsum[w] : 0u;
+        const bool mine = (unsigned)t1 >= run && (unsigned)t0 < run + s;   // a middle rank in this thread's bins
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            const unsigned int c = mine_h[q];
+            if (mine && c) {
+                if ((unsigned)t0 >= run && (unsigned)t0 < run + c) S.ibc[0] = tid * BPT + q;
+                if ((unsigned)t1 >= run && (unsigned)t1 < run + c) S.ibc[1] = tid * BPT + q;
+            }
+            mine_h[q] = run;
+            run += c;
+        }
+        if (tid == kT - 1) S.H[pad(kBins2)] = run;
+        __syncthreads();
+    }
+    if (stop == 3) return;
+    const double w = bin0.width;
+    // one window select: count keys below [lo, hi), list those inside, verify, rank -> S.dbc[0..1]
+    auto window_select = [&](auto key, const double lo, const double hi) -> bool {
+        int below = 0;
+        for_each_value([&](const double x) {
+            const double k = key(x);
+            const bool lt_lo = k < lo, lt_hi = k < hi;         // (nan padding: both false)
+            below += lt_lo ? 1 : 0;
+            if (lt_hi && !lt_lo) list_append2(S, k);           // a few values per row
+        });
+        below = __reduce_add_sync(0xffffffffu, below);
+        if (lane == 0 && below) atomicAdd(&S.below, below);
+        __syncthreads();
+        const int mm = S.list_n, nb_ = S.below;
+        if (mm > kCap2 || t0 < nb_ || t1 >= nb_ + mm) {                     // (uniform)
+            if (tid == 0) atomicAdd(todo_count + (mm > kCap2 ? 8 : (t0 < nb_ ? 9 : 10)), 1u);
+            return false;
+        }
+        rank_list2<kT>(S, mm, nb_, t0, t1);
+        __syncthreads();
+        return true;
+    };
+
+    // ---- pass 2: median ---------------------------------------------------------------------------------
+    const int b0 = S.ibc[0], b1 = S.ibc[1];
+    const double elo = b0 <= 0 ? -INFINITY : bin0.lo + (double)(b0 - 1) * w;
+    const double ehi = b1 >= kBins2 - 1 ? INFINITY : bin0.lo + (double)b1 * w;
+    if (!window_select([](double r) { return r; }, elo, ehi)) { defer(4); return; }
+    const double med = t0 == t1 ? S.dbc[0] : (S.dbc[0] + S.dbc[1]) / 2.0;
+    __syncthreads();                                  // dbc / list / counters are reused
+    if (stop == 4) return;
+
+    // ---- pass 3: MAD ------------------------------------------------------------------------------------
+    // brackets of #{|r - med| < k w} from the prefix table (warp 0)
+    if (warp == 0) {
+        if (lane == 0) { S.list_n = 0; S.below = 0; }
+        const double uu = fmin(fmax((med - bin0.lo) * bin0.scale + 1.0, -4096.0), 8192.0);
+        const int fl = __double2int_rd(uu);
+        auto P = [&](int idx) { return (int)S.H[pad(min(max(idx, 0), kBins2))]; };
+        auto upper = [&](int k) { return k == 0 ? 0 : P(fl + k + 1) - P(fl - k); };
+        auto lower = [&](int k) {                     // whole regular bins only (bins 0 and kBins2-1 are open-ended)
+            const int hi = min(max(fl + k, 1), kBins2 - 1), lo = min(max(fl - k + 1, 1), kBins2 - 1);
+            return hi > lo ? P(hi) - P(lo) : 0;
+        };
+        // three levels (64, 2, 1) cover k < 2048; both predicates are monotone in k
+        static_assert(kBins2 <= 2048, "the bracket search covers 2048 bins");
+        unsigned int m = __ballot_sync(0xffffffffu, upper(64 * lane) <= t0);      // lane 0 always votes
+        int base = 64 * (31 - __clz(m));
+        m = __ballot_sync(0xffffffffu, upper(base + 2 * lane) <= t0);
+        int k_lo = base + 2 * (31 - __clz(m));
+        if (upper(k_lo + 1) <= t0) ++k_lo;
+        m = __ballot_sync(0xffffffffu, lower(64 * lane + 63) > t1);
+        int k_hi = -1;
+        if (m != 0) {
+            base = 64 * (__ffs(m) - 1);
+            m = __ballot_sync(0xffffffffu, lower(base + 2 * lane + 1) > t1);
+            k_hi = base + 2 * (__ffs(m) - 1) + 1;
+            if (lower(k_hi - 1) > t1) --k_hi;
+        }
+        if (lane == 0) { S.ibc[2] = k_lo; S.ibc[3] = k_hi; }
+    }
+    __syncthreads();
+    const int k_lo = S.ibc[2], k_hi = S.ibc[3];
+    if (k_hi < 0) { defer(5); return; }
+    if (stop == 5) return;
+    if (!window_select([med](double r) { return fabs(r - med); }, (double)k_lo * w, (double)k_hi * w)) {
+        defer(6);
+        return;
+    }
+    const double mdev = t0 == t1 ? S.dbc[0] : (S.dbc[0] + S.dbc[1]) / 2.0;
+    if (!(mdev > 1e-300 && mdev < 1e300)) { defer(7); return; }
+    if (stop == 6) return;
+
+    // ---- pass 4: mean of the inliers (fl(d / mdev) < 2  <=>  d < 2 mdev, see the classic kernel) --------
+    // same per-thread order as the classic kernel; the nan padding adds +0.0, which leaves the sum as it is
+    const double thr = 2.0 * mdev;
+    double sum = 0.0;
+    int kept = 0;
+    for_each_value([&](const double x) {
+        const bool keep = fabs(x - med) < thr;
+        sum += keep ? x : 0.0;
+        kept += keep ? 1 : 0;
+    });
+    // the sum as block_sum2 of the classic kernel adds it (identical bits); the count is an integer either way
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    sum = warp_sum(sum);
+    if (lane == 0) { S.red[warp] = sum; atomicAdd(&S.kept, kept); }
+    __syncthreads();
+    if (warp == 0) {
+        sum = warp_sum(lane < NW ? S.red[lane] : 0.0);
+        if (lane == 0) out[slot] = sum / (double)S.kept;
+    }
 }
 
 // Per-row gain from the per-row statistics (reference solex_util.py:400-404, 456-479):
@@ -1016,7 +1411,8 @@ extern "C" int shg_log_table(double* d_tab65536, void* stream) {
 }
 
 static int transv_threads(int max_len) {
-    // enough threads that each owns <= 32 elements (the bit-sliced select), few enough that several rows share an SM
+    // 16 chord positions per thread (measured: 32 per thread in half as many threads is slower, 124 registers); both
+    // kernels of one call use the same count, so their inlier sums associate identically
     int t = max_len <= 4096 ? 128 : (max_len <= 8192 ? 256 : (max_len <= 16384 ? 512 : 1024));
     if (const char* e = getenv("SHG_TRANSV_T")) {            // tuning knob
         const int v = atoi(e);
@@ -1030,12 +1426,18 @@ static int64_t transv_smem_cap(int optin) {
     return ((int64_t)optin - (int64_t)kHeadBytes) / 8;
 }
 
+// workspace: [64 bytes: todo counter, then how many rows came back for reason 1..7][todo list, one uint32 per (image, row)][scratch rows for chords beyond shared memory]
+static int64_t transv_todo_bytes(int n_list, int n_imgs) {
+    return 64 + ((int64_t)n_imgs * n_list * 4 + 15) / 16 * 16;
+}
+
 extern "C" int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs) {
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
-    if (max_len <= transv_smem_cap(optin)) return 0;
-    return (int64_t)n_imgs * n_list * (((int64_t)max_len + 15) / 16 * 16) * 8;
+    const int64_t todo = transv_todo_bytes(n_list, n_imgs);
+    if (max_len <= transv_smem_cap(optin)) return todo;
+    return todo + (int64_t)n_imgs * n_list * (((int64_t)max_len + 15) / 16 * 16) * 8;
 }
 
 extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
@@ -1045,38 +1447,76 @@ extern "C" int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, i
     if (n_list <= 0 || n_imgs <= 0) return 0;
     SHG_REQUIRE(max_len >= 0 && max_len <= cols, "shg_transv_row_stats: max_len %d out of range", max_len);
     SHG_REQUIRE(n_imgs <= 65535, "shg_transv_row_stats: too many images");
+    SHG_REQUIRE((int64_t)n_imgs * n_list < (int64_t)1 << 32, "shg_transv_row_stats: too many rows");
     int dev = 0, optin = 0;
     SHG_CHECK(cudaGetDevice(&dev));
     SHG_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int64_t head = (int64_t)kHeadBytes;
     const int64_t cap = transv_smem_cap(optin);
+    const int64_t todo_bytes = transv_todo_bytes(n_list, n_imgs);
     int64_t pitch = 0;
     size_t smem = (size_t)head;
     if (max_len <= cap) {
         smem += (size_t)max_len * 8;
     } else {
         pitch = ((int64_t)max_len + 15) / 16 * 16;
-        SHG_REQUIRE(d_work && work_bytes >= (int64_t)n_imgs * n_list * pitch * 8,
+        SHG_REQUIRE(d_work && work_bytes >= todo_bytes + (int64_t)n_imgs * n_list * pitch * 8,
                     "shg_transv_row_stats: chords of %d px need %lld bytes of workspace", max_len,
-                    (long long)((int64_t)n_imgs * n_list * pitch * 8));
+                    (long long)(todo_bytes + (int64_t)n_imgs * n_list * pitch * 8));
     }
     const int smem_cap = max_len <= cap ? max_len : 0;
     SHG_REQUIRE(max_len <= cap || transv_threads(max_len) == 1024, "shg_transv_row_stats: internal: %d px chords", max_len);
-    const dim3 grid(n_list, n_imgs);
     cudaStream_t st = as_stream(stream);
     fill_logseg_host();
     SHG_CHECK(cudaMemcpyToSymbolAsync(g_logseg, g_logseg_host, sizeof(g_logseg_host), 0, cudaMemcpyHostToDevice, st));
+    const int threads = transv_threads(max_len);
+    int use_hist = 1;                // SHG_TRANSV_HIST=0: bit-sliced select only; +4 / +8: stop after the rat phase / median (timing)
+    if (const char* e = getenv("SHG_TRANSV_HIST")) use_hist = atoi(e);
+    // the register-resident kernel first (every row of a real scan), the classic kernel for what it hands back;
+    // SHG_TRANSV_REG=0 or SHG_TRANSV_HIST != 1: the classic kernel on every row
+    bool reg = use_hist == 1 && threads >= 128 && max_len <= 32 * threads && d_work && work_bytes >= todo_bytes;
+    if (const char* e = getenv("SHG_TRANSV_REG")) reg = reg && atoi(e) != 0;
+    int stop = 0;                    // SHG_TRANSV_STOP=k: the register-resident kernel returns after phase k (timing only)
+    if (const char* e = getenv("SHG_TRANSV_STOP")) stop = atoi(e);
+    // 16 chord positions per thread in registers; longer chords keep up to 16 more per thread in shared memory
+    const bool spill = max_len > 16 * threads;
+    const size_t reg_smem = spill ? (size_t)16 * threads * sizeof(double) : 0;
+    unsigned int* todo_count = static_cast<unsigned int*>(d_work);
+    uint32_t* todo = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(d_work) + 64);
+    double* scratch = d_work ? reinterpret_cast<double*>(static_cast<unsigned char*>(d_work) + todo_bytes) : nullptr;
+    dim3 grid(n_list, n_imgs);
+    if (reg) {
+        SHG_CHECK(cudaMemsetAsync(todo_count, 0, 64, st));
+#define SHG_TRANSV_REG_LAUNCH(T)                                                                                    \
+        do {                                                                                                        \
+            if (!spill) {                                                                                           \
+                transv_row_stats_reg_kernel<T, 16, 0><<<grid, T, 0, st>>>(d_img, img_stride, cols, d_rows, d_xa,    \
+                                                                           d_xb, n_list, d_out, todo, todo_count,   \
+                                                                           stop);                                   \
+            } else {                                                                                                \
+                SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_reg_kernel<T, 16, 16>,                              \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_smem));        \
+                transv_row_stats_reg_kernel<T, 16, 16><<<grid, T, reg_smem, st>>>(d_img, img_stride, cols, d_rows,  \
+                                                                                   d_xa, d_xb, n_list, d_out, todo, \
+                                                                                   todo_count, stop);               \
+            }                                                                                                       \
+        } while (0)
+        if (threads == 128) SHG_TRANSV_REG_LAUNCH(128);
+        else if (threads == 256) SHG_TRANSV_REG_LAUNCH(256);
+        else if (threads == 512) SHG_TRANSV_REG_LAUNCH(512);
+        else SHG_TRANSV_REG_LAUNCH(1024);
+        SHG_LAUNCH_CHECK();
+        grid = dim3((unsigned)std::min<int64_t>((int64_t)n_list * n_imgs, 2 * SHG_SM_COUNT_B200), 1);
+    }
+    const uint32_t* todo_arg = reg ? todo : nullptr;
 #define SHG_TRANSV_LAUNCH(T)                                                                                        \
     do {                                                                                                            \
         SHG_CHECK(cudaFuncSetAttribute(transv_row_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                        (int)smem));                                                                 \
         transv_row_stats_kernel<T><<<grid, T, smem, st>>>(d_img, img_stride, cols, d_rows, d_xa, d_xb, n_list,      \
-                                                          d_out, static_cast<double*>(d_work), pitch, smem_cap,     \
-                                                          use_hist);                                                \
+                                                          d_out, scratch, pitch, smem_cap, use_hist, todo_arg,      \
+                                                          todo_count);                                              \
     } while (0)
-    const int threads = transv_threads(max_len);
-    int use_hist = 1;                // SHG_TRANSV_HIST=0: bit-sliced select only; +4 / +8: stop after the rat phase / median (timing)
-    if (const char* e = getenv("SHG_TRANSV_HIST")) use_hist = atoi(e);
     if (threads == 64) SHG_TRANSV_LAUNCH(64);
     else if (threads == 128) SHG_TRANSV_LAUNCH(128);
     else if (threads == 256) SHG_TRANSV_LAUNCH(256);

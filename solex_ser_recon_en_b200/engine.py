@@ -785,7 +785,10 @@ class Engine:
         call('shg_transv_row_stats', imgs.data_ptr(), h, w, n_imgs, imgs.stride(0), idx[0].data_ptr(),
              idx[1].data_ptr(), idx[2].data_ptr(), n, max_len, out.data_ptr(),
              _ptr(work), wb, self.stream)
-        self.n_launches += 1
+        # the register-resident kernel, then the classic kernel over the rows it handed back (csrc/transv.cu)
+        classic_only = os.environ.get('SHG_TRANSV_HIST', '1') != '1' or os.environ.get('SHG_TRANSV_REG', '1') == '0'
+        self.n_launches += 1 if classic_only else 2
+        self._transv_work = work           # first word: how many rows went to the classic kernel (diagnostics)
         if device:
             return out
         res = out.cpu().numpy()

@@ -130,6 +130,37 @@ def main():
         ms, best = timed(lambda: eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ), a.reps)
         res['warp'] = dict(ms=ms, best_ms=best, GBps=(img_bytes + oh * ow * 2) / ms / 1e6, out=(oh, ow))
     eng.warp(disk[1], False, mat3, (oh, ow), 300.0, lo, hi, out=circ)
+    if only is not None and 'tbatch' in only:
+        # row statistics of the whole batch alone (the launch of the real step), classic kernel beside it
+        n_img = len(shifts)
+        mm_all = eng.minmax_device(disk)
+        circ_all = eng.empty((n_img, oh, ow), torch.uint16)
+        eng.warp_batch(disk, None, False, mat3, (oh, ow), mm_all, out=circ_all)
+        cy_, cx_, rad_ = oh / 2.0, ow / 2.0, 0.40 * geom.ih
+        y1_, y2_, rows_, xa_, xb_ = eng.transversalium_chords((cx_, cy_, rad_), [0, 0, ow - 1, oh - 1])
+        nbytes = n_img * 2.0 * float((xb_ - xa_).sum()) * 2
+        outs = {}
+        for label, env in (('reg', {}), ('reg_t256', {'SHG_TRANSV_T': '256'}),
+                           ('classic', {'SHG_TRANSV_REG': '0'}), ('bitsliced', {'SHG_TRANSV_HIST': '0'})):
+            os.environ.update(env)
+            ms, best = timed(lambda: eng.transversalium_row_stats(circ_all, rows_, xa_, xb_, device=True), a.reps)
+            outs[label] = eng.transversalium_row_stats(circ_all, rows_, xa_, xb_, device=True)
+            for k in env:
+                del os.environ[k]
+            res['transv_stats_batch_' + label] = dict(ms=ms, best_ms=best, GBps=nbytes / ms / 1e6, rows=len(rows_),
+                                                      images=n_img, max_len=int((xb_ - xa_).max()))
+        for stop in (1, 2, 3, 4, 5, 6):                     # cumulative cost of the phases of the register-resident kernel
+            os.environ['SHG_TRANSV_STOP'] = str(stop)
+            ms, best = timed(lambda: eng.transversalium_row_stats(circ_all, rows_, xa_, xb_, device=True), a.reps)
+            res['reg_stop_after_phase_%d' % stop] = round(ms, 3)
+        del os.environ['SHG_TRANSV_STOP']
+        res['identical_bits'] = dict(reg_vs_classic=bool(torch.equal(outs['reg'], outs['classic'])),
+                                     reg_vs_bitsliced=bool(torch.equal(outs['reg'], outs['bitsliced'])))
+        os.environ['SHG_TRANSV_REG'] = '1'
+        eng.transversalium_row_stats(circ_all, rows_, xa_, xb_, device=True)
+        res['rows_handed_back'] = eng._transv_work[:64].view(torch.int32).tolist()   # total, then per reason (transv.cu)
+        print(json.dumps(dict(config=vars(a), results=res), indent=1))
+        return
     if want('batch'):
         # the launches of the real step: every image of the scan in one call (what profiles/ must show)
         n_img = len(shifts)
