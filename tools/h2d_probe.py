@@ -96,7 +96,7 @@ def main():
     if n >= 4:
         subsets += [[0, 1, 2, 3]]
     if n >= 8:
-        subsets += [[0, 4], [4, 5, 6, 7], list(range(8))]
+        subsets += [[0, 4], list(range(8))]
     out = {'gpus_visible': n, 'host_cpus': os.cpu_count(), 'seconds_per_point': a.seconds, 'buffer_GB': a.gb, 'points': []}
     for devs in subsets:
         for bind in (True, False) if devs == list(range(n)) and n > 1 else (True,):
