@@ -84,6 +84,7 @@ def main():
     ap.add_argument('--seconds', type=float, default=2.0)
     ap.add_argument('--gb', type=float, default=4.0)
     ap.add_argument('--out', default='')
+    ap.add_argument('--subsets', default='', help="e.g. '0,2;0,4' (default: 1, 2, 4, ... GPUs and a far pair)")
     a = ap.parse_args()
     import torch
     n = torch.cuda.device_count()
@@ -97,6 +98,8 @@ def main():
         subsets += [[0, 1, 2, 3]]
     if n >= 8:
         subsets += [[0, 4], list(range(8))]
+    if a.subsets:
+        subsets = [[int(x) for x in grp.split(',')] for grp in a.subsets.split(';')]
     out = {'gpus_visible': n, 'host_cpus': os.cpu_count(), 'seconds_per_point': a.seconds, 'buffer_GB': a.gb, 'points': []}
     for devs in subsets:
         for bind in (True, False) if devs == list(range(n)) and n > 1 else (True,):

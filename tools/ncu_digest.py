@@ -2,7 +2,7 @@
   profiles/<tag>_launches.md       per-kernel share of the bench step (ncu launch list of the bench command)
   profiles/<tag>_<kernel>.txt      headline metrics of each `ncu --set full` capture
   profiles/accumulate_traffic.json DRAM bytes per launch of the dominant kernel (read by bench.py)
-usage: python tools/ncu_digest.py r01"""
+usage: python tools/ncu_digest.py r02"""
 import collections
 import csv
 import json
@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, 'gpurun_out')
 PROF = os.path.join(ROOT, 'profiles')
-tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r02'
 os.makedirs(PROF, exist_ok=True)
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -26,7 +26,8 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__pcsamp_warps_issue_stalled_short_scoreboard', 'smsp__pcsamp_warps_issue_stalled_math_pipe_throttle',
         'smsp__pcsamp_warps_issue_stalled_wait', 'smsp__pcsamp_warps_issue_stalled_not_selected',
         'smsp__pcsamp_warps_issue_stalled_selected', 'smsp__pcsamp_warps_issue_stalled_lg_throttle',
-        'smsp__pcsamp_warps_issue_stalled_mio_throttle']
+        'smsp__pcsamp_warps_issue_stalled_mio_throttle', 'smsp__pcsamp_warps_issue_stalled_no_instructions',
+        'smsp__pcsamp_warps_issue_stalled_branch_resolving']
 
 
 def to_bytes(v, unit):
@@ -34,13 +35,22 @@ def to_bytes(v, unit):
     return float(v) * f
 
 
-def digest_full(path, name):
+def digest_full(path, name, pick=None, note=None):
+    """Headline metrics of one kernel of an ncu report -> profiles/<tag>_<name>.txt.  `pick`: substring of the
+    kernel name (a report may hold several kernels / launches); the LAST matching launch is taken (in
+    tools/kernel_bench.py that is the timed repetition, after the warm-up launches)."""
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
+    hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    lines = ['ncu --set full --clock-control none, one launch inside tools/kernel_bench.py (config-5 geometry)',
-             'kernel: ' + vals[ix['Kernel Name']][:160]]
+    body = [r for r in rows[2:] if len(r) == len(hdr) and (pick is None or pick in r[ix['Kernel Name']])]
+    if not body:
+        return {}
+    vals = body[-1]
+    lines = [note or 'ncu --set full --clock-control none, the production launch inside tools/kernel_bench.py (config-5 '
+             'geometry: whole stack / 101-image batch)',
+             'kernel: ' + vals[ix['Kernel Name']][:160],
+             'launches of this kernel in the report: %d (this is the last)' % len(body)]
     got = {}
     for w in WANT:
         if w in ix:
@@ -48,8 +58,8 @@ def digest_full(path, name):
             got[w] = (vals[ix[w]], units[ix[w]])
     sass = subprocess.run(['cuobjdump', '-sass', os.path.join(ROOT, 'solex_ser_recon_en_b200', 'libshg.so')],
                           capture_output=True, text=True).stdout
-    if name == 'recon_tma':
-        lines.append('SASS evidence of TMA in libshg.so: UTMALDG x%d, SYNCS.ARRIVE.TRANS64 x%d' %
+    if name in ('recon_tma', 'warp_tma'):
+        lines.append('SASS evidence of TMA in libshg.so (all kernels): UTMALDG x%d, SYNCS.ARRIVE.TRANS64 x%d' %
                      (sass.count('UTMALDG'), sass.count('SYNCS.ARRIVE.TRANS64')))
     open(os.path.join(PROF, '%s_%s.txt' % (tag, name)), 'w').write('\n'.join(lines) + '\n')
     return got
@@ -71,7 +81,7 @@ def digest_launches(path):
     setup = {k: v for k, v in agg.items() if 'synth_kernel' in k or 'log_table' in k}
     step = {k: v for k, v in agg.items() if k not in setup}
     tot = sum(v[1] for v in step.values())
-    lines = ['# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e` (config 5, 1 x B200)', '',
+    lines = ['# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-configs` (config 5, 1 x B200)', '',
              '`ncu --metrics gpu__time_duration.sum --clock-control none`: per-launch times are cold-cache and serialised,',
              'so the SHARE of the step is what is comparable with the CUDA-event stage times in the bench line.',
              '3 passes of the step (1 warm-up + 2 timed) + the roofline loop of the accumulate kernel are in the list.', '',
@@ -85,10 +95,19 @@ def digest_launches(path):
 
 if os.path.exists(os.path.join(OUT, 'launches.csv')):
     digest_launches(os.path.join(OUT, 'launches.csv'))
-for name in ('accumulate_u16', 'recon_tma', 'warp_rows', 'transv_row_stats', 'minmax_u16'):
-    p = os.path.join(OUT, 'prof_%s.ncu-rep' % name)
+JOBS = [('accumulate_u16', 'prof_accumulate_u16.ncu-rep', 'accumulate_u16'),
+        ('recon_tma', 'prof_recon_tma.ncu-rep', 'recon_tma_pair'),
+        ('warp_tma', 'prof_batch.ncu-rep', 'warp_tma'),
+        ('row_scale', 'prof_batch.ncu-rep', 'row_scale_kernel'),
+        ('transv_row_stats_reg', 'prof_transv_reg.ncu-rep', 'transv_row_stats_reg'),
+        ('warp_rows', 'prof_warp_rows.ncu-rep', None), ('transv_row_stats', 'prof_transv_row_stats.ncu-rep', None),
+        ('minmax_u16', 'prof_minmax_u16.ncu-rep', None)]
+for name, rep, pick in JOBS:
+    p = os.path.join(OUT, rep)
+    if tag != 'r01' and name in ('warp_rows', 'transv_row_stats', 'minmax_u16'):
+        continue                                   # round-1 captures (kernels since replaced / no longer in the step)
     if os.path.exists(p):
-        got = digest_full(p, name)
+        got = digest_full(p, name, pick)
         if name == 'accumulate_u16' and 'dram__bytes_read.sum' in got:
             rd = to_bytes(*got['dram__bytes_read.sum'])
             wr = to_bytes(*got['dram__bytes_write.sum'])
