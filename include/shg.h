@@ -283,9 +283,13 @@ int shg_log_table(double* d_tab65536, void* stream);
  *   rat = log(img[y][x] / img[y-1][x]);  out[i*n_list + j] = mean(rat[|rat-med|/MAD < 2])
  * (median / MAD as np.median; MAD == 0 keeps all; an empty chord or a nan
  * gives nan as in the reference).  One CTA per (row, image), exact order
- * statistics (counting select, radix select as fall-back) in shared memory.  max_len = max(xb-xa).  Chords
- * longer than shared memory holds use d_work (shg_transv_workspace_bytes; 0 =
- * not needed). */
+ * statistics: a register-resident kernel takes every ordinary row (window selects
+ * whose counts are taken from the data; the MAD window comes from the median's
+ * histogram), and hands the rest (zero pixels, chords <= 256 px, heavy ties) to
+ * the classic kernel (counting select, radix select as fall-back) through a todo
+ * list in d_work.  max_len = max(xb-xa).  d_work: shg_transv_workspace_bytes
+ * bytes (the todo list; plus scratch rows when a chord exceeds shared memory);
+ * without it only the classic kernel runs. */
 int64_t shg_transv_workspace_bytes(int n_list, int max_len, int n_imgs);
 int shg_transv_row_stats(const uint16_t* d_img, int rows, int cols, int n_imgs, int64_t img_stride,
                          const int32_t* d_rows, const int32_t* d_xa, const int32_t* d_xb, int n_list,

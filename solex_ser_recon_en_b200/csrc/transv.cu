@@ -3,23 +3,30 @@
 // Stage 1 (shg_transv_row_stats): for every image row y inside the disk, over
 // the chord [xa, xb):   rat = log(img[y] / img[y-1])
 //                       out = mean(rat[|rat - median(rat)| / MAD < 2])
-// One CTA per (row, image).  rat lives in shared memory (or an L2-resident
-// scratch row for very long chords); the two medians are EXACT order
-// statistics:
-//  * hist_select  -- first choice, rows without zeros: a one-level counting
-//    select (1024 bins from sample quartiles, shared-memory atomics, block scan,
-//    exact fp64 ranking of the few elements in the target bins); the median's
-//    counting pass is fused into the loop that computes the ratios;
-//  * fast_select  -- fall-back for chords of up to 32 elements per thread: binary
-//    radix select over monotone 32-bit keys held bit-sliced in registers;
-//  * block_select -- longer chords / very many ties: fixed-point 5 bits per level.
+// One CTA per (row, image); the two medians are EXACT order statistics.  Two kernels:
+//  * transv_row_stats_reg_kernel (further down) takes every ordinary row: 16 ratios per thread in registers
+//    (the rest of a long chord in shared memory), a 2048-bin histogram, window selects verified by counts
+//    taken from the data, the MAD window derived from the median's histogram; rows it cannot take go to a
+//    todo list;
+//  * transv_row_stats_kernel (the classic kernel: every row when the other is switched off, else a small
+//    persistent grid over the todo list) keeps rat in shared memory (or an L2-resident scratch row for very
+//    long chords) and selects with
+//      hist_select  -- first choice, rows without zeros: a one-level counting
+//        select (1024 bins from sample quartiles, shared-memory atomics, block scan,
+//        exact fp64 ranking of the few elements in the target bins); the median's
+//        counting pass is fused into the loop that computes the ratios;
+//      fast_select  -- fall-back for chords of up to 32 elements per thread: binary
+//        radix select over monotone 32-bit keys held bit-sliced in registers;
+//      block_select -- longer chords / very many ties: fixed-point 5 bits per level.
 // Pixels are uint16 and neighbouring rows differ by noise, so log(a/b) is computed
 // (no table gather): 2 atanh((a-b)/(a+b)) by series for |z| <= 2^-6, else
 // L(a) - L(b) with L = log_u16; both are good to <= ~2e-15 absolute on a quantity
 // of ~1e-2 (the reference's own log(a/b) carries ~1e-16 from the quotient).
 // Stage 2 (shg_row_scale_u16): out = trunc(min(img * gain[row], 65535)).
-// Bound: stage 1 is instruction-bound (~150 instructions per element; its HBM time is 0.5 ms of 5.7 ms
-// at config 5); stage 2 is HBM-bound (each image read once, written once).
+// Bound: stage 1 is instruction-bound (4.0e9 warp instructions for the 101 images of config 5, ~150 per chord
+// element, in either kernel; the register-resident one issues them at 68 % of the slots with 8 rows per SM in
+// flight against 58 % with 6; its HBM time is 0.5 ms of 4.9 ms); stage 2 is HBM-bound (each image read once,
+// written once).
 #include <stdlib.h>
 
 #include <algorithm>
