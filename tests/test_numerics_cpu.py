@@ -1,5 +1,5 @@
-"""CPU models of the two in-kernel logarithms of csrc/transv.cu (log_u16, log_ratio_series): the error bounds
-quoted in the kernel comments and in DESIGN.md, checked in extended precision without a GPU.  The GPU tests
+"""CPU models of the in-kernel logarithms of csrc/transv.cu (log_u16, log_ratio_series) -- the error bounds quoted in
+the kernel comments and in DESIGN.md, checked in extended precision -- and of its two selection schemes, without a GPU.  The GPU tests
 (test_log_u16_matches_numpy, test_row_stats_single_pixel_chords_give_log_ratio) check the kernels themselves."""
 import numpy as np
 
@@ -101,6 +101,95 @@ def test_counting_select_model_is_exact_for_any_bin_edges():
         assert (b0, b1) == (d[t0], d[t1])
         if trial % 2 and trial % 3:
             assert m <= 256                                                # representative edges: short candidate list
+
+
+def _window_select_model(keys, lo, hi, t0, t1, cap=128):
+    """NumPy model of window_select (transv_row_stats_reg_kernel): count the keys below [lo, hi), list those
+    inside, verify that both middle ranks are in the list, rank the list exactly.  None = row handed back."""
+    below = int((keys < lo).sum())
+    cand = np.sort(keys[(keys >= lo) & (keys < hi)])
+    if cand.size > cap or t0 < below or t1 >= below + cand.size:
+        return None
+    return cand[t0 - below], cand[t1 - below], cand.size
+
+
+def _reg_kernel_model(x, qlo, qhi, bins=2048):
+    """Median and MAD as the register-resident row-statistics kernel finds them: histogram of the values only,
+    value window of the middle bins for the median, distance window for the MAD from the SAME histogram's prefix
+    table (no second histogram).  Returns (med, mad, median list length, MAD list length) or None."""
+    n = x.size
+    t0, t1 = (n - 1) // 2, n // 2
+    iqr = qhi - qlo
+    lo, scale, w = qlo - 3.0 * iqr, (bins - 2) / (7.0 * iqr), iqr * (7.0 / (bins - 2))
+    b = np.clip(np.floor((x - lo) * scale + 1.0).astype(np.int64), 0, bins - 1)
+    P = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=bins))])      # P[i] = #values in bins < i
+    b0 = int(np.searchsorted(P, t0, side='right') - 1)
+    b1 = int(np.searchsorted(P, t1, side='right') - 1)
+    elo = -np.inf if b0 <= 0 else lo + (b0 - 1) * w
+    ehi = np.inf if b1 >= bins - 1 else lo + b1 * w
+    got = _window_select_model(x, elo, ehi, t0, t1)
+    if got is None:
+        return None
+    med = got[0] if t0 == t1 else (got[0] + got[1]) / 2.0
+    fl = int(np.floor(min(max((med - lo) * scale + 1.0, -4096.0), 8192.0)))
+
+    def Pc(i):
+        return int(P[min(max(i, 0), bins)])
+
+    def upper(k):                      # every |r - med| < k w lies in bins fl-k .. fl+k
+        return 0 if k == 0 else Pc(fl + k + 1) - Pc(fl - k)
+
+    def lower(k):                      # all of the regular bins fl-k+1 .. fl+k-1 are that close
+        hi_, lo_ = min(max(fl + k, 1), bins - 1), min(max(fl - k + 1, 1), bins - 1)
+        return Pc(hi_) - Pc(lo_) if hi_ > lo_ else 0
+
+    d = np.abs(x - med)
+    for k in (0, 1, 2, 5, 17, 100, 700, 2047):                                # the brackets hold for every k
+        true = int((d < k * w).sum())
+        assert lower(k) <= true <= upper(k), (k, lower(k), true, upper(k))
+    ks = np.arange(bins)
+    k_lo = int(ks[[upper(int(k)) <= t0 for k in ks]].max())
+    ok = [lower(int(k)) > t1 for k in ks]
+    if not any(ok):
+        return None
+    k_hi = int(ks[ok].min())
+    assert k_hi > k_lo
+    got2 = _window_select_model(d, k_lo * w, k_hi * w, t0, t1)
+    if got2 is None:
+        return None
+    mad = got2[0] if t0 == t1 else (got2[0] + got2[1]) / 2.0
+    return med, mad, got[2], got2[2]
+
+
+def test_window_select_with_histogram_brackets_is_exact():
+    """The median's histogram brackets #{|r - med| < k bins} from both sides for every k, so a distance window
+    [k_lo w, k_hi w) that holds both middle ranks of |r - med| follows from it without a second counting pass;
+    counts taken from the data make the result exact whatever the bins are (or the row is handed back)."""
+    rng = np.random.default_rng(12)
+    taken = 0
+    for trial in range(80):
+        n = int(rng.integers(257, 4000))
+        x = rng.normal(0.001, 0.01, n)
+        x[rng.integers(0, n, 30)] = rng.uniform(-2.5, 2.5, 30)            # limb pixels
+        if trial % 4 == 0:
+            x = np.round(x, 3)                                             # heavy ties: lists overflow
+        if trial % 5 == 4:
+            qlo, qhi = sorted(rng.uniform(-0.05, 0.05, 2))                 # a sample that misjudges the row
+        else:
+            s = np.sort(x[((2 * np.arange(32) + 1) * n) >> 6])
+            qlo, qhi = s[8], s[23]
+        if not qhi - qlo >= 1e-5:
+            continue
+        got = _reg_kernel_model(x, qlo, qhi)
+        if got is None:                                                    # handed back to the classic kernel
+            continue
+        taken += 1
+        med, mad, m1, m2 = got
+        assert med == np.median(x)
+        assert mad == np.median(np.abs(x - np.median(x)))
+        if trial % 4 and trial % 5 != 4:
+            assert m1 <= 32 and m2 <= 96                                   # representative bins: short lists
+    assert taken >= 50
 
 
 def test_limb_selection_on_the_sparse_list_equals_the_image_pipeline():
