@@ -104,6 +104,12 @@ def handle_files(files, options, flag_command_line=False):
     except Exception:
         print('ERROR ENCOUNTERED')
         traceback.print_exc()
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            # one rank per GPU: the other ranks are waiting in a collective for this one; carrying on (as the
+            # single-process reference does) would leave them there until NCCL times out -- take the job down
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(1)
 
 
 def is_openable(file):

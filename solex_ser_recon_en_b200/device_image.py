@@ -82,9 +82,10 @@ class DeviceImage:
         return np.flip(self.numpy(), axis=1)
 
     def __getattr__(self, name):
-        # anything else (astype, T, mean, ...) is answered by the host copy
-        if name.startswith('__'):
-            raise AttributeError(name)
+        # any other ndarray attribute (astype, T, mean, ...) is answered by the host copy; a name ndarray does not
+        # have (a typo, a hasattr probe) must not cost a 164 MB device -> host copy before it fails
+        if name.startswith('__') or not hasattr(np.ndarray, name):
+            raise AttributeError('%s object has no attribute %r' % (type(self).__name__, name))
         return getattr(self.numpy(), name)
 
     def _binary(self, other, op):

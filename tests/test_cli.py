@@ -48,3 +48,23 @@ def test_file_arguments(capsys):
     files = C.handle_CLI(o, ['-c', 'a.SER', 'b.avi', 'notes.txt', 'c.ser'])
     assert files == ['a.SER', 'b.avi', 'c.ser']
     assert 'notes.txt was not a valid SER or AVI' in capsys.readouterr().out
+
+
+def test_device_image_unknown_attribute_fails_without_touching_the_pixels():
+    """A name ndarray does not have must raise AttributeError at once: going through the host copy first (as
+    every ndarray attribute legitimately does) would cost a full device -> host copy of the image."""
+    from solex_ser_recon_en_b200.device_image import DeviceImage
+
+    class _NoCopy(DeviceImage):
+        def numpy(self):
+            raise AssertionError('device -> host copy for an attribute probe')
+
+    img = _NoCopy.__new__(_NoCopy)
+    assert getattr(img, 'not_an_ndarray_attribute', None) is None
+    assert not hasattr(img, 'fitfuture')
+    try:
+        img.astype                                            # a real ndarray attribute does go to the host copy
+    except AssertionError:
+        pass
+    else:
+        raise AssertionError('astype should have asked for the host copy')
