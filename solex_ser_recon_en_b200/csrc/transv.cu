@@ -861,10 +861,12 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
 
 // ---------------------------------------------------------------------------
 // Register-resident row statistics (the launch every real scan takes).
-// A thread keeps its E = 16 ratios in REGISTERS (element e of thread t is chord position e*kT + t), so the
-// passes after the first are straight-line code with no shared-memory traffic for the values, and shared
-// memory (7 KB) no longer limits residency: 4 CTAs of 256 threads per SM at <= 64 registers.
-//   pass 1  ratios + 1024-bin counts (bins from sample quartiles, as above); block scan -> prefix table P
+// A thread keeps 16 ratios in REGISTERS (element e of thread t is chord position e*kT + t) and the rest of a chord
+// longer than 16 kT in shared memory, so the passes after the first are straight-line code over registers plus a
+// short loop, and residency is 8 CTAs of 128 threads per SM (64 registers, 10 KB static + 16 KB dynamic shared
+// memory) against 6 for the classic kernel.  Throughput here is rows in flight / latency of one row: a version with
+// 256 threads and 4 rows per SM executed fewer instructions and was slower.
+//   pass 1  ratios + 2048-bin counts (bins from sample quartiles); block scan -> prefix table P
 //   pass 2  WINDOW SELECT for the median: the value window [lo, hi) of the bin(s) holding the middle ranks;
 //           every thread counts its values below the window and appends those inside to a list; the list is
 //           ranked exactly in fp64.  The counts are taken from the data, so the result does not depend on
@@ -873,13 +875,16 @@ transv_row_stats_kernel(const uint16_t* __restrict__ img_base, int64_t img_strid
 //   pass 3  WINDOW SELECT for the MAD without a second histogram: with u = position of the median in bin
 //           units, the values with |r - med| < k bins lie in bins floor(u)-k .. floor(u)+k, and all values of
 //           bins floor(u)-k+1 .. floor(u)+k-1 are that close, so P brackets the count for every k: the
-//           largest k_lo with upper(k_lo) <= t0 and the smallest k_hi with lower(k_hi) > t1 (two ballots
-//           each) give a distance window [k_lo w, k_hi w) that holds both middle ranks; same count / collect
-//           / verify / rank as pass 2, on the keys |r - med|.
+//           largest k_lo with upper(k_lo) <= t0 and the smallest k_hi with lower(k_hi) > t1 (a three-level
+//           search, two ballots each) give a distance window [k_lo w, k_hi w) that holds both middle ranks;
+//           same count / collect / verify / rank as pass 2, on the keys |r - med|.
+//           (tests/test_numerics_cpu.py: test_window_select_with_histogram_brackets_is_exact models passes 2-3.)
 //   pass 4  mean of the inliers, in the same per-thread order and with the same block reduction as the
 //           classic kernel (identical bits: test_row_stats_counting_select_equals_bitsliced).
-// Rows this cannot take (a zero pixel, chords <= 256 or > 16 kT, ties that overflow a list, an
+// Rows this cannot take (a zero pixel, chords <= 256 or > 32 kT, ties that overflow a list, an
 // unrepresentative sample, MAD == 0) are appended to a todo list and done by the classic kernel above.
+// The values must stay in registers: anything that makes the compiler spill them (four interleaved chains per
+// group instead of two, a noinline call for the rare log path) turns every later pass into a wait on local memory.
 constexpr int kBins2 = 2048;
 constexpr int kCap2 = 128;            // candidate list (a few dozen with bins this fine)
 constexpr int kMinLen2 = 256;         // shorter chords: the classic kernel ranks everything
@@ -899,7 +904,8 @@ struct Shared2 {
 
 // Bins of the register-resident kernel: kBins2 - 2 regular bins over the sample's inter-quartile range widened by
 // 3 IQR each side (a 32-value sample can misjudge the spread by a factor of two and med +- MAD still lies inside;
-// whatever falls outside goes to the two open bins), i.e. a bin is IQR/292 wide: a handful of values per bin at the centre of a 3000-pixel chord.
+// whatever falls outside goes to the two open bins), i.e. a bin is IQR/292 wide: a handful of values per bin at the
+// centre of a 3000-pixel chord.
 struct HistBins2 {
     double lo, scale, magic, width;
     __device__ __forceinline__ void set(double qlo, double qhi) {

@@ -1,6 +1,6 @@
 """Record the N=1 outputs_crc of a bench line as the expected value for THIS build (profiles/outputs_crc.json).
 
-    python tools/record_crc.py gpurun_out/bench_n1.log
+    python tools/record_crc.py gpurun_out/bench_n1.log [note]
 
 `bench.py --record-crc` does the same on the machine that ran the bench; a gpurun box only returns gpurun_out/, so
 the value is taken from the returned bench line here.  The record is binding for runs of the same sources only
@@ -24,6 +24,8 @@ try:
 except Exception:
     book = {}
 book[key] = {'crc': line['outputs_crc'], 'n_gpus': 1, 'source_sha': bench.source_sha()}
+if len(sys.argv) > 2:                      # e.g. what changed in the sources since the run the line comes from
+    book[key]['note'] = sys.argv[2]
 with open(bench.CRC_FILE, 'w') as f:
     json.dump(book, f, indent=1, sort_keys=True)
 print(key, book[key])
